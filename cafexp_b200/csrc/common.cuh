@@ -1,0 +1,147 @@
+// Shared definitions for the sm_100a kernels of the birth-death likelihood engine.
+#pragma once
+
+#include <cstdint>
+#include <cuda_runtime.h>
+
+namespace cafe {
+
+// ---------------------------------------------------------------------------------------------
+// Geometry of the pruning kernel.  A thread block prunes FT families ("columns") of one rate
+// category through the whole tree; every partial-likelihood vector lives in shared memory as
+// V[family][size] with a padded stride so that FP64 MMA B-fragments load without bank conflicts.
+// ---------------------------------------------------------------------------------------------
+constexpr int FT = 32;                  // families per tile (MMA N dimension = 4 n8 blocks)
+constexpr int CONSUMER_WARPS = 8;       // 4 (rows) x 2 (family columns)
+constexpr int CONSUMER_THREADS = CONSUMER_WARPS * 32;
+constexpr int PRUNE_THREADS = CONSUMER_THREADS + 32;   // + 1 producer warp issuing bulk copies
+constexpr int STAGES = 4;               // ring of matrix K-chunks
+constexpr int PPS = 2;                  // K panels (of 4 columns) per stage
+constexpr int CNT_CAP_BYTES = 8192;     // staged leaf counts (uint16) per tile, if they fit
+constexpr int LGAMMA_TABLE = 1024;      // src/probability.cpp:52
+constexpr int MAX_SLOTS = 8;
+constexpr int MAX_MB = 8;               // rows padded to NR = 32*MB <= 256
+
+__host__ __device__ constexpr int nr_of(int mb) { return 32 * mb; }
+__host__ __device__ constexpr int ldv_of(int mb) { return 32 * mb + 4; }            // stride % 16 == 4 (8-byte words)
+__host__ __device__ constexpr int stage_doubles(int mb) { return PPS * 4 * 32 * mb; }
+
+// Schedule op codes (host-built, one list per tree; see build_schedule in cafe_b200.cu)
+enum : int {
+    OP_LEAF_SET = 0,   // V[a] = column obs of M(node)            (leaf child, first factor of its parent)
+    OP_LEAF_MUL = 1,   // V[a] *= column obs of M(node)
+    OP_GEMM_SET = 2,   // V[a] = M(node) * V[a]                   (internal child, first factor)
+    OP_GEMM_MUL = 3,   // V[a] *= M(node) * V[b]
+    OP_SPILL = 4,      // scratch[b] = V[a]
+    OP_FILL = 5,       // V[a] = scratch[b]
+    OP_RESCALE = 6,    // per-family power-of-two renormalisation of V[a]
+    OP_ROOT = 7        // root prior / category weight, write results
+};
+
+struct Op {
+    int type;
+    int a;
+    int b;
+    int node;
+};
+
+struct PruneParams {
+    // problem
+    int64_t n_families;
+    int n_leaves;
+    int n_nodes;
+    int n_categories;
+    int mf;                 // max_family_size
+    int mrf;                // max_root_family_size
+    int n_ops;
+    int n_kchunks;          // K chunks per GEMM (each PPS*4 columns)
+    int mode;
+    int rescale;
+    int n_spill;            // scratch vectors per block
+    int err_rows;
+    int err_ndev;
+    int counts_in_smem;
+    int n_slots;
+    int64_t n_tiles;
+    // device pointers
+    const Op* ops;
+    const int32_t* counts;          // [F][n_leaves]
+    const int* leaf_col;            // [n_nodes]
+    const int* mat_of;              // [k][n_nodes] -> unique matrix slot
+    const double* mp;               // panelised matrices   [U][kpanels][NR][4]
+    const double* mt;               // transposed matrices  [U][mf+1][NR]
+    size_t mp_stride;               // doubles per matrix
+    size_t mt_stride;
+    const double* err;              // [err_rows][err_ndev] or null
+    const double* prior;            // [mrf]
+    const double* logprior;         // [mrf]
+    const double* cat_probs;        // [k]
+    double* scratch;                // [grid][n_spill][FT*LDV]
+    int* scratch_exp;               // [grid][n_spill][FT]
+    // outputs
+    double* cat_lk;                 // [F][k]   (gamma)  or family lnL [F] (base)
+    uint8_t* fail;                  // [F][k]
+    double* root_out;               // [F][k][mrf] or null (inspection)
+};
+
+// ---------------------------------------------------------------------------------------------
+// PTX helpers: mbarrier, bulk async copy (TMA engine, 1-D), FP64 tensor-core MMA.
+// ---------------------------------------------------------------------------------------------
+__device__ __forceinline__ uint32_t smem_u32(const void* p) { return static_cast<uint32_t>(__cvta_generic_to_shared(p)); }
+
+__device__ __forceinline__ void mbar_init(uint64_t* bar, uint32_t count)
+{
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count));
+}
+
+__device__ __forceinline__ void fence_barrier_init()
+{
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+}
+
+__device__ __forceinline__ void mbar_arrive(uint64_t* bar)
+{
+    asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(bar)) : "memory");
+}
+
+__device__ __forceinline__ void mbar_arrive_expect_tx(uint64_t* bar, uint32_t bytes)
+{
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes) : "memory");
+}
+
+__device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity)
+{
+    asm volatile(
+        "{\n"
+        ".reg .pred p;\n"
+        "WAIT_LOOP:\n"
+        "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n"
+        "@p bra WAIT_DONE;\n"
+        "bra WAIT_LOOP;\n"
+        "WAIT_DONE:\n"
+        "}\n" ::"r"(smem_u32(bar)),
+        "r"(parity)
+        : "memory");
+}
+
+// 1-D bulk copy global -> shared through the TMA engine; completion is signalled on the mbarrier.
+__device__ __forceinline__ void bulk_copy_g2s(void* smem_dst, const void* gmem_src, uint32_t bytes, uint64_t* bar)
+{
+    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(smem_u32(smem_dst)),
+                 "l"(gmem_src), "r"(bytes), "r"(smem_u32(bar))
+                 : "memory");
+}
+
+// D(8x8) += A(8x4, row) * B(4x8, col) on the FP64 tensor pipe (SASS: DMMA).
+// lane l holds A[l/4][l%4], B[l%4][l/4], D[l/4][2*(l%4) + {0,1}].
+__device__ __forceinline__ void dmma_m8n8k4(double& d0, double& d1, double a, double b)
+{
+    asm volatile("mma.sync.aligned.m8n8k4.row.col.f64.f64.f64.f64 {%0,%1}, {%2}, {%3}, {%0,%1};" : "+d"(d0), "+d"(d1) : "d"(a), "d"(b));
+}
+
+__device__ __forceinline__ void consumer_sync()
+{
+    asm volatile("bar.sync 1, %0;" ::"n"(CONSUMER_THREADS) : "memory");
+}
+
+}  // namespace cafe

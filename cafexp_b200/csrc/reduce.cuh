@@ -1,0 +1,79 @@
+// Kernel 3b — per-family finalisation and the deterministic reduction of sum_i lnL_i.
+//
+// Restates (file:line in the reference)
+//   gamma: family_likelihood = accumulate(cat_likelihoods), lnL = log(.)        src/gamma_core.cpp:207,218
+//          any failed family -> the evaluation returns -log(0)                    src/gamma_core.cpp:227-236
+//   base : lnL_i already produced by the root op; score = -accumulate(lnL)        src/base_model.cpp:107
+//
+// The reference adds the per-family values serially in family order; here each block adds its
+// slice in a fixed tree order and one block adds the block partials in index order, so the result
+// is run-to-run deterministic and differs from the serial sum only by reassociation (~1e-16 rel).
+// Bound: HBM (reads k doubles + k flags, writes one double per family) — a few MB, latency-sized.
+#pragma once
+
+#include "common.cuh"
+
+namespace cafe {
+
+constexpr int RED_THREADS = 256;
+
+__global__ void __launch_bounds__(RED_THREADS) finalize_kernel(int64_t n_families, int k, int mode, const double* __restrict__ cat_lk,
+                                                               const uint8_t* __restrict__ fail, double* __restrict__ family_lnl,
+                                                               uint8_t* __restrict__ family_fail, double* __restrict__ partial)
+{
+    __shared__ double s_sum[RED_THREADS];
+    __shared__ double s_bad[RED_THREADS];
+    double sum = 0.0, bad = 0.0;
+    for (int64_t i = (int64_t)blockIdx.x * RED_THREADS + threadIdx.x; i < n_families; i += (int64_t)gridDim.x * RED_THREADS) {
+        double lnl;
+        bool failed = false;
+        if (mode == 0) lnl = cat_lk[i];
+        else {
+            double fam = 0.0;
+            for (int c = 0; c < k; ++c) {
+                failed |= fail[i * k + c] != 0;
+                fam += cat_lk[i * k + c];
+            }
+            lnl = log(fam);
+        }
+        if (failed) { lnl = __longlong_as_double(0x7ff8000000000000LL); bad += 1.0; }
+        else sum += lnl;
+        family_lnl[i] = lnl;
+        family_fail[i] = failed ? 1 : 0;
+    }
+    s_sum[threadIdx.x] = sum;
+    s_bad[threadIdx.x] = bad;
+    __syncthreads();
+    for (int off = RED_THREADS / 2; off > 0; off >>= 1) {
+        if (threadIdx.x < off) {
+            s_sum[threadIdx.x] += s_sum[threadIdx.x + off];
+            s_bad[threadIdx.x] += s_bad[threadIdx.x + off];
+        }
+        __syncthreads();
+    }
+    if (threadIdx.x == 0) {
+        partial[2 * blockIdx.x] = s_sum[0];
+        partial[2 * blockIdx.x + 1] = s_bad[0];
+    }
+}
+
+__global__ void __launch_bounds__(RED_THREADS) final_sum_kernel(int n_partials, const double* __restrict__ partial, double* __restrict__ result)
+{
+    __shared__ double s_sum[RED_THREADS];
+    __shared__ double s_bad[RED_THREADS];
+    double sum = 0.0, bad = 0.0;
+    for (int i = threadIdx.x; i < n_partials; i += RED_THREADS) { sum += partial[2 * i]; bad += partial[2 * i + 1]; }
+    s_sum[threadIdx.x] = sum;
+    s_bad[threadIdx.x] = bad;
+    __syncthreads();
+    for (int off = RED_THREADS / 2; off > 0; off >>= 1) {
+        if (threadIdx.x < off) {
+            s_sum[threadIdx.x] += s_sum[threadIdx.x + off];
+            s_bad[threadIdx.x] += s_bad[threadIdx.x + off];
+        }
+        __syncthreads();
+    }
+    if (threadIdx.x == 0) { result[0] = s_sum[0]; result[1] = s_bad[0]; }
+}
+
+}  // namespace cafe

@@ -1,0 +1,161 @@
+/* cafe_b200.h — C ABI of the B200-native (sm_100a) per-family birth-death likelihood engine.
+ *
+ * This is the drop-in boundary for ONE hot path of Han9527/CAFExp (CAFE5): everything
+ * model::infer_family_likelihoods and model::reconstruct_ancestral_states compute below the host
+ * orchestration.  The reference has no FFI layer; its seam is the C++ virtuals
+ *      model::infer_family_likelihoods          src/core.h:171
+ *      model::reconstruct_ancestral_states      src/core.h:179
+ *      optimizer_scorer::calculate_score        src/optimizer_scorer.h:22
+ * and the entry points below are what CUDA-backed subclasses of base_model / gamma_model call
+ * (integration/cuda_models.cpp; binding notes in INTEGRATION.md).
+ *
+ * Conventions
+ *   - plain C, opaque handle, int status (0 = ok, <0 = error; cafe_b200_last_error() has the text),
+ *     no exceptions cross the boundary, every output buffer is caller-owned HOST memory unless the
+ *     name says _device.
+ *   - one host thread per context (as the reference: every call comes from the Nelder-Mead thread).
+ *   - numerical failure is reported in-band like the reference: *neg_lnl = +inf and *n_failed > 0,
+ *     never as an error status.
+ *   - there is NO CPU fallback: without a CUDA device every compute entry point returns
+ *     CAFE_B200_ERR_CUDA.
+ */
+#ifndef CAFE_B200_H
+#define CAFE_B200_H
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define CAFE_B200_ABI_VERSION 1
+
+enum {
+    CAFE_B200_OK = 0,
+    CAFE_B200_ERR_ARG = -1,         /* bad argument (null pointer, size, tree shape)                 */
+    CAFE_B200_ERR_CUDA = -2,        /* CUDA runtime error or no device                               */
+    CAFE_B200_ERR_COUNT_RANGE = -3, /* a leaf count (+ error-model deviation) is outside 0..max_family_size:
+                                       the reference would index past its vectors (src/probability.cpp:191,197) */
+    CAFE_B200_ERR_LIMIT = -4        /* size beyond what this build supports (see cafe_b200_limits)   */
+};
+
+/* mode of cafe_b200_eval */
+enum {
+    CAFE_B200_BASE_LOGMAX = 0,  /* base_model: lnL_i = max_j(log L_i[j] + log prior[j])         src/base_model.cpp:89-106 */
+    CAFE_B200_GAMMA_LINSUM = 1  /* gamma_model: lnL_i = log sum_k max_j(L_ik[j] prior[j]) catprob[k], fail if sum_j L_ik[j]==0
+                                                                                                  src/gamma_core.cpp:144-166,203-219 */
+};
+
+/* options for cafe_b200_set_option */
+enum {
+    CAFE_B200_OPT_RESCALE = 1   /* 0 (default): reference arithmetic, partial likelihoods may underflow exactly as in the
+                                   reference.  1: exact power-of-two per-family rescaling of every internal-node vector;
+                                   identical results wherever the reference does not underflow, and the reference's
+                                   "all zero" failure verdict is reproduced from the tracked exponent. */
+};
+
+/* Species tree, flattened.  Node numbering = the order clade::apply_reverse_level_order visits
+ * (src/clade.cpp:255-280): children before parents, root last.  Children in Newick order
+ * (clade::_descendants).  n-ary nodes are allowed. */
+typedef struct cafe_b200_tree {
+    int n_nodes;
+    const int* parent;         /* [n_nodes]  -1 for the root                                              */
+    const int* child_offset;   /* [n_nodes+1] CSR offsets into child_list                                  */
+    const int* child_list;     /* [n_nodes-1]                                                              */
+    const int* leaf_col;       /* [n_nodes]  column of the count matrix for a leaf, -1 for internal nodes  */
+    const double* branch;      /* [n_nodes]  RAW branch length; quantised inside as matrix_cache_key does
+                                             (long(t*1000)/1000.0, src/matrix_cache.h:50,58)               */
+    const int* lambda_index;   /* [n_nodes]  0-based index of the lambda that applies to the branch above
+                                             the node (multiple_lambda's node-name map, src/lambda.cpp:32-40) */
+} cafe_b200_tree;
+
+typedef struct cafe_b200_ctx cafe_b200_ctx;
+
+typedef struct cafe_b200_limits {
+    int max_matrix_size;       /* max(max_family_size, max_root_family_size)+1 supported      */
+    int max_categories;
+    int max_nodes;
+    int families_per_tile;     /* families pruned together as matrix columns by one thread block */
+} cafe_b200_limits;
+
+int  cafe_b200_abi_version(void);
+void cafe_b200_get_limits(cafe_b200_limits* out);
+
+/* Number of CUDA devices visible (0 without a driver/GPU). */
+int  cafe_b200_device_count(void);
+
+/* Replaces the model constructor's view of (tree, families, max sizes): src/core.h:59-70.
+ * leaf_counts: HOST [n_families][n_leaves] int32, column = tree->leaf_col; copied to the device.
+ * device: CUDA ordinal.  The context owns one stream; all work of a call is enqueued on it. */
+int  cafe_b200_create(cafe_b200_ctx** out, const cafe_b200_tree* tree, const int32_t* leaf_counts,
+                      int64_t n_families, int n_leaves, int max_family_size, int max_root_family_size, int device);
+void cafe_b200_destroy(cafe_b200_ctx* ctx);
+const char* cafe_b200_last_error(const cafe_b200_ctx* ctx);   /* ctx may be NULL: last create() error */
+
+/* Re-upload the count matrix (same shape as at create).  Replaces model::set_families (src/core.h:148). */
+int  cafe_b200_set_families(cafe_b200_ctx* ctx, const int32_t* leaf_counts, int64_t n_families);
+
+/* Leaf error model: dense HOST [rows][n_deviations] table indexed by OBSERVED count, i.e. row s =
+ * error_model::get_probs(s) (src/error_model.cpp:52-57); deviations are centred, -(nd-1)/2..+(nd-1)/2
+ * (src/probability.cpp:185).  probs == NULL removes the error model. */
+int  cafe_b200_set_error_model(cafe_b200_ctx* ctx, const double* probs, int rows, int n_deviations);
+
+int  cafe_b200_set_option(cafe_b200_ctx* ctx, int option, int value);
+
+/* Use an existing CUDA stream (cudaStream_t passed as void*) instead of the context's own. */
+int  cafe_b200_set_stream(cafe_b200_ctx* ctx, void* cuda_stream);
+
+/* One evaluation of the likelihood = the body of base_model::infer_family_likelihoods
+ * (src/base_model.cpp:77-107) or gamma_model::infer_family_likelihoods (src/gamma_core.cpp:196-244):
+ * builds every transition matrix for (branch, lambda, category) on the device, prunes every family,
+ * applies root prior / category weights, reduces.
+ *   lambdas    HOST [n_categories][n_lambdas] RAW values lambda_i * multiplier_k (multiply first as
+ *              lambda::multiply does, src/lambda.h:47,80); quantised inside (long(x*1e9)/1e9).
+ *   cat_probs  HOST [n_categories] (gamma_cat_probs; {1.0} for the base model)
+ *   prior      HOST [max_root_family_size]: (double)prior->compute(j), j = 0..mrf-1 (a float widened)
+ *   neg_lnl    out: -sum_i lnL_i, or +inf when the reference returns -log(0)
+ *   family_lnl out HOST [n_families] or NULL (NaN for failed families)
+ *   cat_lk     out HOST [n_families][n_categories] or NULL (gamma mode: _category_likelihoods)
+ *   n_failed   out: families whose pruning "saturated" (gamma mode), may be NULL
+ *   failed_idx out HOST [failed_cap] first indices of failed families, may be NULL */
+int  cafe_b200_eval(cafe_b200_ctx* ctx, const double* lambdas, int n_lambdas, const double* cat_probs, int n_categories,
+                    const double* prior, int mode, double* neg_lnl, double* family_lnl, double* cat_lk,
+                    int64_t* n_failed, int64_t* failed_idx, int64_t failed_cap);
+
+/* Same evaluation, asynchronous, result left on the device: result_device[0] = sum_i lnL_i over
+ * non-failed families, result_device[1] = number of failed families (as a double).  This is the pair a
+ * multi-process caller sum-allreduces (NCCL) across its family shards; no host synchronisation. */
+int  cafe_b200_eval_device(cafe_b200_ctx* ctx, const double* lambdas, int n_lambdas, const double* cat_probs, int n_categories,
+                           const double* prior, int mode, double* result_device);
+
+/* Pupko joint ancestral reconstruction = reconstruct_gene_family for every family and category
+ * (src/gene_family_reconstructor.cpp:13-165; callers src/base_model.cpp:145-162, src/gamma_core.cpp:301-347).
+ *   prior_by_size HOST [min(mf,mrf)+1]: (double)prior->compute(size) — indexed by the size itself
+ *   states  out HOST [n_families][n_categories][n_internal] int32, internal nodes in tree order (root last) */
+int  cafe_b200_reconstruct(cafe_b200_ctx* ctx, const double* lambdas, int n_lambdas, int n_categories,
+                           const double* prior_by_size, int32_t* states);
+
+/* ---- inspection entry points used by the parity tests ------------------------------------- */
+
+/* Transition matrices as the device built them: HOST out [n_categories][n_nodes][N][max_family_size+1]
+ * (row = parent size, col = child size <= max_family_size; the root's block is zero), N = matrix size.
+ * Replaces matrix_cache::precalculate_matrices + get_matrix (src/matrix_cache.cpp:121-171, :80-97). */
+int  cafe_b200_build_matrices(cafe_b200_ctx* ctx, const double* lambdas, int n_lambdas, int n_categories, double* out);
+int  cafe_b200_matrix_size(const cafe_b200_ctx* ctx);
+
+/* Root partial-likelihood vectors = inference_prune (src/core.cpp:133-144):
+ * HOST out [n_families][n_categories][max_root_family_size], index j <-> root size j+1. */
+int  cafe_b200_prune_roots(cafe_b200_ctx* ctx, const double* lambdas, int n_lambdas, int n_categories, double* out);
+
+/* Counters since create: kernel launches issued by this library, and evaluations. */
+int64_t cafe_b200_launch_count(const cafe_b200_ctx* ctx);
+
+/* Device time (ms, CUDA events on the context's stream) of the phases of the LAST cafe_b200_eval /
+ * cafe_b200_prune_roots / cafe_b200_reconstruct call: [0] matrix build, [1] pruning, [2] reduce,
+ * [3] reconstruction.  Valid after the call returned (it synchronises). */
+int  cafe_b200_last_timings(const cafe_b200_ctx* ctx, double* ms4);
+
+#ifdef __cplusplus
+}
+#endif
+#endif
