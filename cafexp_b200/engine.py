@@ -1,0 +1,251 @@
+"""ctypes binding of the C ABI in include/cafe_b200.h (cafexp_b200/libcafe_b200.so).
+
+This is the thinnest possible layer: numpy arrays in, numpy arrays out, every call goes to the CUDA
+library.  There is no CPU fallback — if the library has not been built (``__graft_entry__.build()``)
+or no CUDA device is visible, the calls raise.
+"""
+from __future__ import annotations
+
+import ctypes as C
+import math
+import os
+from typing import Optional
+
+import numpy as np
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+LIB_PATH = os.path.join(HERE, "libcafe_b200.so")
+
+BASE_LOGMAX = 0
+GAMMA_LINSUM = 1
+OPT_RESCALE = 1
+
+ERR_NAMES = {-1: "ERR_ARG", -2: "ERR_CUDA", -3: "ERR_COUNT_RANGE", -4: "ERR_LIMIT"}
+
+#: every symbol include/cafe_b200.h declares (tests check the library exports all of them)
+EXPORTS = [
+    "cafe_b200_abi_version", "cafe_b200_get_limits", "cafe_b200_device_count", "cafe_b200_create", "cafe_b200_destroy",
+    "cafe_b200_last_error", "cafe_b200_set_families", "cafe_b200_set_error_model", "cafe_b200_set_option", "cafe_b200_set_stream",
+    "cafe_b200_eval", "cafe_b200_eval_device", "cafe_b200_reconstruct", "cafe_b200_build_matrices", "cafe_b200_matrix_size",
+    "cafe_b200_prune_roots", "cafe_b200_launch_count", "cafe_b200_last_timings",
+]
+
+_dp = C.POINTER(C.c_double)
+_ip = C.POINTER(C.c_int)
+_i32p = C.POINTER(C.c_int32)
+_i64p = C.POINTER(C.c_int64)
+
+
+class CafeB200Error(RuntimeError):
+    pass
+
+
+class _Tree(C.Structure):
+    _fields_ = [("n_nodes", C.c_int), ("parent", _ip), ("child_offset", _ip), ("child_list", _ip),
+                ("leaf_col", _ip), ("branch", _dp), ("lambda_index", _ip)]
+
+
+class _Limits(C.Structure):
+    _fields_ = [("max_matrix_size", C.c_int), ("max_categories", C.c_int), ("max_nodes", C.c_int), ("families_per_tile", C.c_int)]
+
+
+_lib = None
+
+
+def load_library():
+    """Load libcafe_b200.so; raises if it was not built (no silent fallback)."""
+    global _lib
+    if _lib is not None:
+        return _lib
+    if not os.path.exists(LIB_PATH):
+        raise CafeB200Error(f"{LIB_PATH} is missing: run `python -c 'import __graft_entry__ as g; g.build()'` "
+                            "(nvcc, sm_100a). cafexp_b200 has no CPU fallback.")
+    L = C.CDLL(LIB_PATH)
+    L.cafe_b200_abi_version.restype = C.c_int
+    L.cafe_b200_get_limits.argtypes = [C.POINTER(_Limits)]
+    L.cafe_b200_device_count.restype = C.c_int
+    L.cafe_b200_create.restype = C.c_int
+    L.cafe_b200_create.argtypes = [C.POINTER(C.c_void_p), C.POINTER(_Tree), _i32p, C.c_int64, C.c_int, C.c_int, C.c_int, C.c_int]
+    L.cafe_b200_destroy.argtypes = [C.c_void_p]
+    L.cafe_b200_last_error.restype = C.c_char_p
+    L.cafe_b200_last_error.argtypes = [C.c_void_p]
+    L.cafe_b200_set_families.restype = C.c_int
+    L.cafe_b200_set_families.argtypes = [C.c_void_p, _i32p, C.c_int64]
+    L.cafe_b200_set_error_model.restype = C.c_int
+    L.cafe_b200_set_error_model.argtypes = [C.c_void_p, _dp, C.c_int, C.c_int]
+    L.cafe_b200_set_option.restype = C.c_int
+    L.cafe_b200_set_option.argtypes = [C.c_void_p, C.c_int, C.c_int]
+    L.cafe_b200_set_stream.restype = C.c_int
+    L.cafe_b200_set_stream.argtypes = [C.c_void_p, C.c_void_p]
+    L.cafe_b200_eval.restype = C.c_int
+    L.cafe_b200_eval.argtypes = [C.c_void_p, _dp, C.c_int, _dp, C.c_int, _dp, C.c_int, _dp, _dp, _dp, _i64p, _i64p, C.c_int64]
+    L.cafe_b200_eval_device.restype = C.c_int
+    L.cafe_b200_eval_device.argtypes = [C.c_void_p, _dp, C.c_int, _dp, C.c_int, _dp, C.c_int, C.c_void_p]
+    L.cafe_b200_reconstruct.restype = C.c_int
+    L.cafe_b200_reconstruct.argtypes = [C.c_void_p, _dp, C.c_int, C.c_int, _dp, _i32p]
+    L.cafe_b200_build_matrices.restype = C.c_int
+    L.cafe_b200_build_matrices.argtypes = [C.c_void_p, _dp, C.c_int, C.c_int, _dp]
+    L.cafe_b200_matrix_size.restype = C.c_int
+    L.cafe_b200_matrix_size.argtypes = [C.c_void_p]
+    L.cafe_b200_prune_roots.restype = C.c_int
+    L.cafe_b200_prune_roots.argtypes = [C.c_void_p, _dp, C.c_int, C.c_int, _dp]
+    L.cafe_b200_launch_count.restype = C.c_int64
+    L.cafe_b200_launch_count.argtypes = [C.c_void_p]
+    L.cafe_b200_last_timings.restype = C.c_int
+    L.cafe_b200_last_timings.argtypes = [C.c_void_p, _dp]
+    if L.cafe_b200_abi_version() != 1:
+        raise CafeB200Error("libcafe_b200.so ABI version mismatch")
+    _lib = L
+    return L
+
+
+def device_count() -> int:
+    return load_library().cafe_b200_device_count()
+
+
+def limits() -> dict:
+    lim = _Limits()
+    load_library().cafe_b200_get_limits(C.byref(lim))
+    return {name: getattr(lim, name) for name, _ in _Limits._fields_}
+
+
+def _d(a):
+    return a.ctypes.data_as(_dp)
+
+
+class Engine:
+    """One context = one (tree, family shard, size limits) on one GPU; mirrors what a reference
+    ``model`` object holds between evaluations (src/core.h:122-186)."""
+
+    def __init__(self, tree, counts: np.ndarray, max_family_size: int, max_root_family_size: int, device: int = 0):
+        L = load_library()
+        self._lib = L
+        self.tree = tree
+        self._arrays = [np.ascontiguousarray(tree.parent, np.int32), np.ascontiguousarray(tree.child_offset, np.int32),
+                        np.ascontiguousarray(tree.child_list, np.int32), np.ascontiguousarray(tree.leaf_col, np.int32),
+                        np.ascontiguousarray(tree.branch, np.float64), np.ascontiguousarray(tree.lambda_index, np.int32)]
+        a = self._arrays
+        ts = _Tree(len(a[0]), a[0].ctypes.data_as(_ip), a[1].ctypes.data_as(_ip), a[2].ctypes.data_as(_ip), a[3].ctypes.data_as(_ip),
+                   _d(a[4]), a[5].ctypes.data_as(_ip))
+        counts = np.ascontiguousarray(counts, np.int32)
+        if counts.ndim != 2 or counts.shape[1] != tree.n_leaves:
+            raise ValueError("counts must be [n_families, n_leaves]")
+        self.n_families = int(counts.shape[0])
+        self.n_leaves = int(counts.shape[1])
+        self.n_internal = int((np.asarray(tree.leaf_col) < 0).sum())
+        self.mf = int(max_family_size)
+        self.mrf = int(max_root_family_size)
+        self.device = device
+        handle = C.c_void_p()
+        rc = L.cafe_b200_create(C.byref(handle), C.byref(ts), counts.ctypes.data_as(_i32p), self.n_families, self.n_leaves,
+                                self.mf, self.mrf, device)
+        if rc != 0:
+            raise CafeB200Error(f"cafe_b200_create: {ERR_NAMES.get(rc, rc)}: {L.cafe_b200_last_error(None).decode()}")
+        self._h = handle
+        self.matrix_size = L.cafe_b200_matrix_size(self._h)
+
+    # -- lifetime -------------------------------------------------------------------------------
+    def close(self):
+        if getattr(self, "_h", None):
+            self._lib.cafe_b200_destroy(self._h)
+            self._h = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    def __enter__(self):
+        return self
+
+    def __exit__(self, *exc):
+        self.close()
+
+    def _check(self, rc, what):
+        if rc != 0:
+            raise CafeB200Error(f"{what}: {ERR_NAMES.get(rc, rc)}: {self._lib.cafe_b200_last_error(self._h).decode()}")
+
+    # -- configuration --------------------------------------------------------------------------
+    def set_families(self, counts: np.ndarray):
+        counts = np.ascontiguousarray(counts, np.int32)
+        self._check(self._lib.cafe_b200_set_families(self._h, counts.ctypes.data_as(_i32p), counts.shape[0]), "set_families")
+
+    def set_error_model(self, table: Optional[np.ndarray]):
+        if table is None:
+            self._check(self._lib.cafe_b200_set_error_model(self._h, None, 0, 0), "set_error_model")
+            return
+        t = np.ascontiguousarray(table, np.float64)
+        self._check(self._lib.cafe_b200_set_error_model(self._h, _d(t), t.shape[0], t.shape[1]), "set_error_model")
+
+    def set_rescale(self, on: bool):
+        self._check(self._lib.cafe_b200_set_option(self._h, OPT_RESCALE, 1 if on else 0), "set_option")
+
+    def set_stream(self, cuda_stream_ptr: int):
+        self._check(self._lib.cafe_b200_set_stream(self._h, C.c_void_p(cuda_stream_ptr)), "set_stream")
+
+    # -- the hot path ---------------------------------------------------------------------------
+    @staticmethod
+    def _lams(lambdas):
+        lam = np.ascontiguousarray(np.atleast_2d(np.asarray(lambdas, np.float64)))
+        return lam, lam.shape[0], lam.shape[1]
+
+    def infer(self, lambdas, prior, cat_probs=None, mode=BASE_LOGMAX, want_family=True, want_cat=True, failed_cap=1024):
+        """One likelihood evaluation.  lambdas: [k][n_lambdas] raw lambda_i*multiplier_k."""
+        lam, k, nl = self._lams(lambdas)
+        cp = np.ascontiguousarray(cat_probs if cat_probs is not None else np.ones(k), np.float64)
+        pr = np.ascontiguousarray(prior, np.float64)
+        if pr.shape[0] < self.mrf:
+            raise ValueError("prior must have max_root_family_size entries")
+        score = C.c_double()
+        nf = C.c_int64()
+        fam = np.empty(self.n_families) if want_family else None
+        cat = np.empty((self.n_families, k)) if (want_cat and mode == GAMMA_LINSUM) else None
+        fidx = np.full(failed_cap, -1, np.int64)
+        rc = self._lib.cafe_b200_eval(self._h, _d(lam), nl, _d(cp), k, _d(pr), mode, C.byref(score),
+                                      _d(fam) if fam is not None else None, _d(cat) if cat is not None else None,
+                                      C.byref(nf), fidx.ctypes.data_as(_i64p), failed_cap)
+        self._check(rc, "cafe_b200_eval")
+        return {"score": score.value, "family_lnl": fam, "cat_lk": cat, "n_failed": nf.value, "failed_idx": fidx[fidx >= 0]}
+
+    def infer_device(self, lambdas, prior, cat_probs, mode, result_ptr: int):
+        """Asynchronous evaluation; [sum lnL, n_failed] are written to device memory at result_ptr."""
+        lam, k, nl = self._lams(lambdas)
+        cp = np.ascontiguousarray(cat_probs if cat_probs is not None else np.ones(k), np.float64)
+        pr = np.ascontiguousarray(prior, np.float64)
+        self._check(self._lib.cafe_b200_eval_device(self._h, _d(lam), nl, _d(cp), k, _d(pr), mode, C.c_void_p(result_ptr)), "cafe_b200_eval_device")
+
+    def reconstruct(self, lambdas, prior_by_size):
+        lam, k, nl = self._lams(lambdas)
+        pr = np.ascontiguousarray(prior_by_size, np.float64)
+        if pr.shape[0] < min(self.mf, self.mrf) + 1:
+            raise ValueError("prior_by_size must have min(mf, mrf)+1 entries")
+        states = np.empty((self.n_families, k, self.n_internal), np.int32)
+        self._check(self._lib.cafe_b200_reconstruct(self._h, _d(lam), nl, k, _d(pr), states.ctypes.data_as(_i32p)), "cafe_b200_reconstruct")
+        return states
+
+    # -- inspection -----------------------------------------------------------------------------
+    def build_matrices(self, lambdas):
+        lam, k, nl = self._lams(lambdas)
+        out = np.empty((k, self.tree.n_nodes, self.matrix_size, self.mf + 1))
+        self._check(self._lib.cafe_b200_build_matrices(self._h, _d(lam), nl, k, _d(out)), "cafe_b200_build_matrices")
+        return out
+
+    def prune_roots(self, lambdas):
+        lam, k, nl = self._lams(lambdas)
+        out = np.empty((self.n_families, k, self.mrf))
+        self._check(self._lib.cafe_b200_prune_roots(self._h, _d(lam), nl, k, _d(out)), "cafe_b200_prune_roots")
+        return out
+
+    @property
+    def launches(self) -> int:
+        return int(self._lib.cafe_b200_launch_count(self._h))
+
+    def last_timings_ms(self) -> dict:
+        ms = np.zeros(4)
+        self._lib.cafe_b200_last_timings(self._h, _d(ms))
+        return {"matrix_build": ms[0], "prune": ms[1], "reduce": ms[2], "reconstruct": ms[3]}
+
+
+def neg_inf_safe(x: float) -> float:
+    return math.inf if math.isnan(x) else x

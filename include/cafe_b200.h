@@ -48,10 +48,12 @@ enum {
 
 /* options for cafe_b200_set_option */
 enum {
-    CAFE_B200_OPT_RESCALE = 1   /* 0 (default): reference arithmetic, partial likelihoods may underflow exactly as in the
+    CAFE_B200_OPT_RESCALE = 1,  /* 0 (default): reference arithmetic, partial likelihoods may underflow exactly as in the
                                    reference.  1: exact power-of-two per-family rescaling of every internal-node vector;
                                    identical results wherever the reference does not underflow, and the reference's
                                    "all zero" failure verdict is reproduced from the tracked exponent. */
+    CAFE_B200_OPT_MAX_SLOTS = 2 /* cap the shared-memory vector slots per thread block (>= 2; default: as many as fit).
+                                   Fewer slots force the schedule to spill vectors to device scratch; used by tests. */
 };
 
 /* Species tree, flattened.  Node numbering = the order clade::apply_reverse_level_order visits
@@ -146,6 +148,11 @@ int  cafe_b200_matrix_size(const cafe_b200_ctx* ctx);
 /* Root partial-likelihood vectors = inference_prune (src/core.cpp:133-144):
  * HOST out [n_families][n_categories][max_root_family_size], index j <-> root size j+1. */
 int  cafe_b200_prune_roots(cafe_b200_ctx* ctx, const double* lambdas, int n_lambdas, int n_categories, double* out);
+
+/* Host-only (no GPU needed): the op list the pruning / reconstruction kernels walk for this tree with
+ * n_slots shared-memory slots.  ops_out: [cap][4] = {type, a, b, node}; types: 0 LEAF_SET(a,node) 1 LEAF_MUL
+ * 2 GEMM_SET(a,node) 3 GEMM_MUL(a,b,node) 4 SPILL(a->scratch b) 5 FILL(a<-scratch b) 6 RESCALE(a) 7 ROOT(a). */
+int  cafe_b200_plan_schedule(const cafe_b200_tree* tree, int n_slots, int* ops_out, int cap, int* n_ops, int* n_spill);
 
 /* Counters since create: kernel launches issued by this library, and evaluations. */
 int64_t cafe_b200_launch_count(const cafe_b200_ctx* ctx);

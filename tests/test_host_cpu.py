@@ -1,0 +1,161 @@
+"""CPU-only checks of the host side: the C ABI library loads and exports what include/cafe_b200.h declares,
+refuses to compute without a GPU, and the schedule the kernels walk reproduces inference_prune when it is
+interpreted on the CPU with oracle-built matrices (this validates slot allocation, spilling and child order)."""
+import ctypes as C
+import os
+import re
+
+import numpy as np
+import pytest
+
+from conftest import ROOT
+from cafexp_b200 import engine, hostio, synth
+from oracle import binding as orc
+
+OPS = {0: "LEAF_SET", 1: "LEAF_MUL", 2: "GEMM_SET", 3: "GEMM_MUL", 4: "SPILL", 5: "FILL", 6: "RESCALE", 7: "ROOT"}
+
+
+def test_library_exports_every_declared_symbol():
+    lib = engine.load_library()
+    header = open(os.path.join(ROOT, "include", "cafe_b200.h")).read()
+    declared = set(re.findall(r"\b(cafe_b200_[a-z_]+)\s*\(", header))
+    declared -= {"cafe_b200_limits"}
+    assert declared, "no declarations parsed"
+    for name in sorted(declared):
+        assert hasattr(lib, name), f"{name} declared in include/cafe_b200.h but not exported"
+    assert declared == set(engine.EXPORTS) | {"cafe_b200_plan_schedule"}
+    assert lib.cafe_b200_abi_version() == 1
+    lim = engine.limits()
+    assert lim["families_per_tile"] == 32 and lim["max_matrix_size"] >= 151
+
+
+@pytest.mark.skipif(engine.load_library().cafe_b200_device_count() > 0, reason="a GPU is present")
+def test_no_cpu_fallback():
+    """Without a CUDA device the product path must fail loudly, not compute on the host."""
+    tree = hostio.flatten_tree(hostio.parse_newick("(A:1,B:1);"))
+    with pytest.raises(engine.CafeB200Error, match="no CUDA device"):
+        engine.Engine(tree, np.array([[1, 2]], np.int32), 10, 8)
+
+
+def test_create_rejects_bad_input():
+    lib = engine.load_library()
+    handle = C.c_void_p()
+    assert lib.cafe_b200_create(C.byref(handle), None, None, 0, 0, 0, 0, 0) == -1
+
+
+def plan(tree, n_slots):
+    lib = engine.load_library()
+    lib.cafe_b200_plan_schedule.restype = C.c_int
+    arrs = [np.ascontiguousarray(a, np.int32) for a in (tree.parent, tree.child_offset, tree.child_list, tree.leaf_col)]
+    br = np.ascontiguousarray(tree.branch, np.float64)
+    li = np.ascontiguousarray(tree.lambda_index, np.int32)
+    ip = C.POINTER(C.c_int)
+    ts = engine._Tree(tree.n_nodes, arrs[0].ctypes.data_as(ip), arrs[1].ctypes.data_as(ip), arrs[2].ctypes.data_as(ip),
+                      arrs[3].ctypes.data_as(ip), br.ctypes.data_as(C.POINTER(C.c_double)), li.ctypes.data_as(ip))
+    cap = 16 * tree.n_nodes + 64
+    ops = np.zeros((cap, 4), np.int32)
+    n_ops = C.c_int()
+    n_spill = C.c_int()
+    rc = lib.cafe_b200_plan_schedule(C.byref(ts), n_slots, ops.ctypes.data_as(ip), cap, C.byref(n_ops), C.byref(n_spill))
+    assert rc == 0
+    return ops[:n_ops.value], n_spill.value
+
+
+def interpret(tree, ops, n_slots, counts_row, lambdas, mf, mrf):
+    """Run the schedule on the CPU for one family: what the pruning kernel does, in numpy."""
+    n = max(mf, mrf) + 1
+    mats = {}
+    for v in range(tree.n_nodes - 1):
+        mats[v] = orc.build_matrix(n, lambdas[tree.lambda_index[v]], tree.branch[v])[:, :mf + 1]
+    slots = [None] * n_slots
+    scratch = {}
+    for typ, a, b, node in ops:
+        name = OPS[int(typ)]
+        if name in ("LEAF_SET", "LEAF_MUL"):
+            col = mats[node][:, counts_row[tree.leaf_col[node]]]
+            slots[a] = col.copy() if name == "LEAF_SET" else slots[a] * col
+        elif name == "GEMM_SET":
+            assert a == b
+            slots[a] = mats[node] @ slots[a][:mf + 1]
+        elif name == "GEMM_MUL":
+            assert a != b and slots[a] is not None and slots[b] is not None
+            slots[a] = slots[a] * (mats[node] @ slots[b][:mf + 1])
+            slots[b] = None
+        elif name == "SPILL":
+            scratch[b] = slots[a]
+            slots[a] = None
+        elif name == "FILL":
+            assert slots[a] is None
+            slots[a] = scratch.pop(b)
+        elif name == "ROOT":
+            return slots[a][1:mrf + 1]
+    raise AssertionError("no ROOT op")
+
+
+TREES = {
+    "cherry": "(A:1,B:1);",
+    "abcd": "((A:1,B:1):1,(C:1,D:1):1);",
+    "caterpillar": "((((A:1,B:2):1.5,C:3):2,D:4):1,E:7);",
+    "tri": "((A:2,B:1.5,C:3):1,D:4,(E:1,F:1):2);",
+    "balanced16": "((((A:1,B:1):1,(C:1,D:1):1):1,((E:1,F:1):1,(G:1,H:1):1):1):1,(((I:1,J:1):1,(K:1,L:1):1):1,((M:1,N:1):1,(O:1,P:1):1):1):1);",
+}
+
+
+@pytest.mark.parametrize("name", sorted(TREES))
+@pytest.mark.parametrize("n_slots", [2, 3, 4, 8])
+def test_schedule_reproduces_inference_prune(name, n_slots):
+    tree = hostio.flatten_tree(hostio.parse_newick(TREES[name]))
+    ops, n_spill = plan(tree, n_slots)
+    types = [OPS[int(t)] for t in ops[:, 0]]
+    assert types[-1] == "ROOT" and types.count("ROOT") == 1
+    internal_children = sum(1 for v in range(tree.n_nodes - 1) if tree.leaf_col[v] < 0)
+    assert types.count("GEMM_SET") + types.count("GEMM_MUL") == internal_children
+    assert types.count("LEAF_SET") + types.count("LEAF_MUL") == tree.n_leaves
+    assert types.count("SPILL") == types.count("FILL")
+    assert all(0 <= a < n_slots for t, a, b, _ in ops if OPS[int(t)] != "SPILL" or True)
+    if name == "balanced16" and n_slots == 2:
+        assert n_spill > 0, "a balanced tree with two slots must spill"
+    if n_slots >= 5:
+        assert n_spill == 0
+    rng = np.random.default_rng(3)
+    mf, mrf = 14, 10
+    lam = [0.04]
+    for _ in range(3):
+        row = rng.integers(0, 7, tree.n_leaves).astype(np.int32)
+        got = interpret(tree, ops, n_slots, row, lam, mf, mrf)
+        want = orc.inference_prune(tree, row, lam, mf, mrf)
+        np.testing.assert_allclose(got, want, rtol=1e-12, atol=0)
+
+
+def test_schedule_on_config5_tree_spills_at_most_once_with_four_slots():
+    newick = synth.random_ultrametric_newick(100, 12345)
+    tree = hostio.flatten_tree(hostio.parse_newick(newick))
+    assert tree.n_nodes == 199 and tree.n_leaves == 100
+    ops, n_spill = plan(tree, 4)          # 4 slots is what fits in 227 KB at N = 151
+    types = [OPS[int(t)] for t in ops[:, 0]]
+    assert n_spill <= 1 and types.count("SPILL") <= 1
+    assert types.count("GEMM_SET") + types.count("GEMM_MUL") == 98
+    assert plan(tree, 5)[1] == 0
+
+
+def test_nary_children_keep_newick_order():
+    tree = hostio.flatten_tree(hostio.parse_newick(TREES["tri"]))
+    ops, _ = plan(tree, 8)
+    root = tree.n_nodes - 1
+    kids = list(tree.child_list[tree.child_offset[root]:tree.child_offset[root + 1]])
+    # the ops that fold each root child into the root accumulator appear in Newick order
+    fold = [int(node) for t, a, b, node in ops if int(node) in kids and OPS[int(t)] in ("LEAF_SET", "LEAF_MUL", "GEMM_SET", "GEMM_MUL")]
+    assert fold == kids
+
+
+def test_mammal_host_preparation(mammal):
+    """Root filter, size limits and traversal order as the reference computes them (12 653 -> 10 956 families,
+    mf 140, mrf 112)."""
+    assert mammal["counts_all"].shape == (12653, 12)
+    assert mammal["counts"].shape[0] == 10956
+    assert np.array_equal(np.flatnonzero(mammal["keep"]), mammal["gold"]["keep"])
+    assert (mammal["mf"], mammal["mrf"]) == (140, 112)
+    assert mammal["tree"].n_nodes == 23 and mammal["tree2"].n_lambdas == 2
+    names = mammal["tree2"].names
+    lam_idx = dict(zip(names, mammal["tree2"].lambda_index))
+    assert lam_idx["chimp"] == 1 and lam_idx["human"] == 1 and lam_idx["chimphuman"] == 1 and lam_idx["orang"] == 0
