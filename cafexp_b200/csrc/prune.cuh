@@ -168,6 +168,7 @@ __global__ void __launch_bounds__(PRUNE_THREADS, 1) prune_kernel(const PrunePara
                     if (op.type == OP_LEAF_SET) {
                         #pragma unroll
                         for (int i = 0; i < MB; ++i) row[lane + 32 * i] = v[i];
+                        if (lane == 0) slot_exp[op.a * FT + f] = 0;     // fresh vector in a recycled slot
                     }
                     else {
                         #pragma unroll
@@ -245,6 +246,7 @@ __global__ void __launch_bounds__(PRUNE_THREADS, 1) prune_kernel(const PrunePara
             }
             case OP_RESCALE: {
                 // exact power-of-two renormalisation per family: V *= 2^-e, exponent tracked in slot_exp
+                if (!p.rescale) break;          // uniform: reference arithmetic, no renormalisation
                 double* sl = slots + (size_t)op.a * L::SLOT_DOUBLES;
                 #pragma unroll
                 for (int fi = 0; fi < FT / CONSUMER_WARPS; ++fi) {
