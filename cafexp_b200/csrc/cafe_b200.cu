@@ -779,7 +779,7 @@ int cafe_b200_set_stream(cafe_b200_ctx* c, void* cuda_stream)
     if (!c) return CAFE_B200_ERR_ARG;
     CUDA_TRY(c, cudaSetDevice(c->device));
     CUDA_TRY(c, cudaStreamSynchronize(c->stream));
-    c->stream = cuda_stream ? (cudaStream_t)cuda_stream : c->own_stream;
+    c->stream = (cudaStream_t)cuda_stream;          // NULL is the legacy default stream, as in the CUDA runtime
     CUDA_TRY(c, cudaEventRecord(c->staged, c->stream));
     return CAFE_B200_OK;
 }

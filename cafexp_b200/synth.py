@@ -67,51 +67,70 @@ def bd_transition_matrix(lam: float, t: float, n: int) -> np.ndarray:
     return m
 
 
-def simulate_families(tree: hostio.FlatTree, n_families: int, lam: float = 0.005, seed: int = 12345, root_mean: float = 10.0,
-                      max_count: int = 100, state_cap: int = 151, chunk: int = 262144) -> np.ndarray:
-    """int32 counts [n_families, n_leaves]; every leaf count <= max_count and the family is present on
-    both sides of the root (the reference's default filter, src/cafexp.cpp:189-199)."""
-    rng = np.random.default_rng(seed)
-    n = tree.n_nodes
+GEN_CHUNK = 65536
+
+
+def _branch_cdfs(tree: hostio.FlatTree, lam: float, state_cap: int):
     mats = {}
-    for v in range(n - 1):
+    for v in range(tree.n_nodes - 1):
         key = round(float(tree.branch[v]), 6)
         if key not in mats:
             cdf = np.cumsum(bd_transition_matrix(lam, key, state_cap), axis=1)
             cdf[:, -1] = 1.0
             # one sorted array for all rows: row s occupies (2s, 2s+1]
             mats[key] = (cdf + 2.0 * np.arange(state_cap)[:, None]).ravel()
-    out = np.empty((n_families, tree.n_leaves), np.int32)
+    return mats
+
+
+def _simulate_chunk(tree, mats, rng, want: int, root_mean: float, max_count: int, state_cap: int) -> np.ndarray:
+    n = tree.n_nodes
+    leaves = np.flatnonzero(tree.leaf_col >= 0)
+    out = np.empty((want, tree.n_leaves), np.int32)
     filled = 0
-    root_children = tree.child_list[tree.child_offset[n - 1]:tree.child_offset[n]]
-    while filled < n_families:
-        m = min(chunk, max(1024, int((n_families - filled) * 1.1) + 16))
+    while filled < want:
+        m = max(1024, int((want - filled) * 1.1) + 16)
         state = np.zeros((n, m), np.int32)
-        state[n - 1] = 1 + rng.poisson(root_mean, m)
-        np.minimum(state[n - 1], max_count, out=state[n - 1])
+        state[n - 1] = np.minimum(1 + rng.poisson(root_mean, m), max_count)
         for v in range(n - 2, -1, -1):
             parent = state[tree.parent[v]]
             flat = mats[round(float(tree.branch[v]), 6)]
-            u = rng.random(m)
-            idx = np.searchsorted(flat, u + 2.0 * parent, side="left")
+            idx = np.searchsorted(flat, rng.random(m) + 2.0 * parent, side="left")
             state[v] = np.minimum(idx - parent * state_cap, state_cap - 1)
-        leaves = np.flatnonzero(tree.leaf_col >= 0)
         counts = np.empty((m, tree.n_leaves), np.int32)
         counts[:, tree.leaf_col[leaves]] = state[leaves].T
-        ok = counts.max(axis=1) <= max_count
-        ok &= hostio.exists_at_root(tree, counts)
+        ok = (counts.max(axis=1) <= max_count) & hostio.exists_at_root(tree, counts)
         counts = counts[ok]
-        take = min(len(counts), n_families - filled)
+        take = min(len(counts), want - filled)
         out[filled:filled + take] = counts[:take]
         filled += take
     return out
 
 
-def config5(n_families: int, n_leaves: int = 100, seed: int = 12345, lam: float = 0.005) -> Tuple[hostio.FlatTree, np.ndarray, str]:
-    """(tree, counts, newick) of the synthetic benchmark; max_family_size=150, max_root_family_size=125 by construction."""
+def simulate_families(tree: hostio.FlatTree, n_families: int, lam: float = 0.005, seed: int = 12345, root_mean: float = 10.0,
+                      max_count: int = 100, state_cap: int = 151, first: int = 0, last: int = -1) -> np.ndarray:
+    """int32 counts [last-first, n_leaves] = families first..last-1 of the n_families-family data set.
+
+    Every leaf count <= max_count and every family is present on both sides of the root (the reference's
+    default filter, src/cafexp.cpp:189-199).  Families are generated in independent chunks of GEN_CHUNK
+    (seeded by (seed, chunk index)), so any rank can produce exactly its shard of the same global data set."""
+    if last < 0:
+        last = n_families
+    mats = _branch_cdfs(tree, lam, state_cap)
+    parts = []
+    for chunk in range(first // GEN_CHUNK, (max(last, first + 1) - 1) // GEN_CHUNK + 1):
+        lo, hi = chunk * GEN_CHUNK, min((chunk + 1) * GEN_CHUNK, n_families)
+        rng = np.random.default_rng([seed, chunk])
+        block = _simulate_chunk(tree, mats, rng, hi - lo, root_mean, max_count, state_cap)
+        parts.append(block[max(first, lo) - lo:min(last, hi) - lo])
+    return np.concatenate(parts) if parts else np.zeros((0, tree.n_leaves), np.int32)
+
+
+def config5(n_families: int, n_leaves: int = 100, seed: int = 12345, lam: float = 0.005, first: int = 0, last: int = -1
+            ) -> Tuple[hostio.FlatTree, np.ndarray, str]:
+    """(tree, counts[first:last], newick) of the synthetic benchmark; max_family_size=150, max_root_family_size=125."""
     newick = random_ultrametric_newick(n_leaves, seed)
     tree = hostio.flatten_tree(hostio.parse_newick(newick))
-    counts = simulate_families(tree, n_families, lam=lam, seed=seed)
+    counts = simulate_families(tree, n_families, lam=lam, seed=seed, first=first, last=last)
     return tree, counts, newick
 
 

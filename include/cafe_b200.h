@@ -104,7 +104,8 @@ int  cafe_b200_set_error_model(cafe_b200_ctx* ctx, const double* probs, int rows
 
 int  cafe_b200_set_option(cafe_b200_ctx* ctx, int option, int value);
 
-/* Use an existing CUDA stream (cudaStream_t passed as void*) instead of the context's own. */
+/* Enqueue on an existing CUDA stream (cudaStream_t passed as void*; NULL = the legacy default stream)
+ * instead of the context's own non-blocking stream. */
 int  cafe_b200_set_stream(cafe_b200_ctx* ctx, void* cuda_stream);
 
 /* One evaluation of the likelihood = the body of base_model::infer_family_likelihoods
