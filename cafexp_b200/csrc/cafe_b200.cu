@@ -33,6 +33,10 @@ struct Schedule {
     int n_spill = 0;
 };
 
+struct FusedOp {
+    int type, a, b, node, node2;
+};
+
 struct HostTree {
     int n_nodes = 0;
     std::vector<int> parent, child_offset, child_list, leaf_col, lambda_index;
@@ -213,6 +217,26 @@ const char* import_tree(HostTree& t, const cafe_b200_tree* tree, int n_leaves)
     return nullptr;
 }
 
+// Peephole over the schedule (pruning without error model): a leaf sibling that directly follows is
+// folded into the producing op.  The products formed are the same two-operand products in the same
+// order, so results are bit-identical to the unfused schedule.
+//   LEAF_SET(a,l1) LEAF_MUL(a,l2)  -> LEAF_SET2(a,l1,l2)
+//   GEMM_SET(a,c)  LEAF_MUL(a,l)   -> GEMM_SET_LEAF(a,c,l)
+// GEMM_MUL is never fused: (f1*f2)*leaf must not become f1*(f2*leaf).
+std::vector<FusedOp> fuse_schedule(const std::vector<Op>& ops, bool fuse)
+{
+    std::vector<FusedOp> out;
+    for (size_t i = 0; i < ops.size(); ++i) {
+        const Op& o = ops[i];
+        if (fuse && i + 1 < ops.size() && ops[i + 1].type == OP_LEAF_MUL && ops[i + 1].a == o.a) {
+            if (o.type == OP_LEAF_SET) { out.push_back({OP_LEAF_SET2, o.a, 0, o.node, ops[i + 1].node}); ++i; continue; }
+            if (o.type == OP_GEMM_SET) { out.push_back({OP_GEMM_SET_LEAF, o.a, o.b, o.node, ops[i + 1].node}); ++i; continue; }
+        }
+        out.push_back({o.type, o.a, o.b, o.node, -1});
+    }
+    return out;
+}
+
 template <typename T>
 cudaError_t dev_alloc(T** p, size_t n, bool zero = false)
 {
@@ -234,7 +258,8 @@ struct cafe_b200_ctx {
     int64_t n_families = 0;
     int64_t n_tiles = 0;
     int max_count = 0;
-    Schedule sched;
+    Schedule sched;                     // unfused ops: reconstruction kernel, pruning with an error model
+    std::vector<FusedOp> fused;         // fused ops: pruning without error model
     int n_slots = 0;
     int hw_slots = 0;
     int rescale = 0;
@@ -243,6 +268,9 @@ struct cafe_b200_ctx {
     // device buffers
     int32_t* d_counts = nullptr;
     Op* d_ops = nullptr;
+    POp* d_pops = nullptr;              // [cap_k][pops_cap] per-category resolved pruning ops
+    int pops_cap = 0;
+    int n_pops = 0;                     // ops per category in the last staged evaluation
     int* d_leaf_col = nullptr;
     int* d_parent = nullptr;
     int* d_child_offset = nullptr;
@@ -297,7 +325,8 @@ int ensure_category_buffers(cafe_b200_ctx* c, int k)
 {
     if (k <= c->cap_k) return CAFE_B200_OK;
     cudaFree(c->d_mat_of); cudaFree(c->d_mp); cudaFree(c->d_mt); cudaFree(c->d_keys); cudaFree(c->d_powc);
-    cudaFree(c->d_cat_lk); cudaFree(c->d_fail); cudaFree(c->d_catprobs);
+    cudaFree(c->d_cat_lk); cudaFree(c->d_fail); cudaFree(c->d_catprobs); cudaFree(c->d_pops);
+    c->d_pops = nullptr;
     c->d_mat_of = nullptr; c->d_mp = c->d_mt = nullptr; c->d_keys = nullptr; c->d_powc = nullptr;
     c->d_cat_lk = nullptr; c->d_fail = nullptr; c->d_catprobs = nullptr;
     c->cap_k = 0;
@@ -310,8 +339,11 @@ int ensure_category_buffers(cafe_b200_ctx* c, int k)
     CUDA_TRY(c, dev_alloc(&c->d_cat_lk, (size_t)c->n_families * k));
     CUDA_TRY(c, dev_alloc(&c->d_fail, (size_t)c->n_families * k, true));
     CUDA_TRY(c, dev_alloc(&c->d_catprobs, (size_t)k));
-    // staging: keys + powc + mat_of + prior + logprior + catprobs
-    size_t need = keys * sizeof(KeyParams) + keys * c->n * sizeof(double) + keys * sizeof(int) + (2 * (size_t)c->n + k + 64) * sizeof(double);
+    c->pops_cap = (int)c->sched.ops.size();
+    CUDA_TRY(c, dev_alloc(&c->d_pops, (size_t)k * c->pops_cap));
+    // staging: keys + powc + mat_of + prior + logprior + catprobs + per-category ops
+    size_t need = keys * sizeof(KeyParams) + keys * c->n * sizeof(double) + keys * sizeof(int) + (2 * (size_t)c->n + k + 64) * sizeof(double)
+                  + (size_t)k * c->pops_cap * sizeof(POp) + 64;
     if (need > c->h_stage_bytes) {
         if (c->h_stage) cudaFreeHost(c->h_stage);
         c->h_stage = nullptr;
@@ -373,6 +405,22 @@ int stage_and_build(cafe_b200_ctx* c, const double* lambdas, int n_lambdas, int 
         h_logprior[j] = std::log(pj);                                        // src/base_model.cpp:98
     }
     for (int cat = 0; cat < k; ++cat) h_cat[cat] = cat_probs ? cat_probs[cat] : 1.0;
+    // per-category pruning ops with matrix slots and count columns resolved
+    POp* h_pops = reinterpret_cast<POp*>((reinterpret_cast<uintptr_t>(h_mat_of + slots) + 15) & ~uintptr_t(15));   // POp is 16-byte aligned
+    if ((int)c->sched.ops.size() > c->pops_cap) return fail(c, CAFE_B200_ERR_ARG, "schedule grew after the category buffers were sized");
+    const std::vector<FusedOp> plain = c->d_err ? fuse_schedule(c->sched.ops, false) : std::vector<FusedOp>();
+    const std::vector<FusedOp>& fo = c->d_err ? plain : c->fused;
+    c->n_pops = (int)fo.size();
+    for (int cat = 0; cat < k; ++cat)
+        for (int o = 0; o < c->n_pops; ++o) {
+            POp q;
+            q.type = fo[o].type; q.a = fo[o].a; q.b = fo[o].b; q.node = fo[o].node;
+            q.mat = h_mat_of[cat * t.n_nodes + fo[o].node];
+            q.col = t.leaf_col[fo[o].node];
+            q.mat2 = fo[o].node2 >= 0 ? h_mat_of[cat * t.n_nodes + fo[o].node2] : 0;
+            q.col2 = fo[o].node2 >= 0 ? t.leaf_col[fo[o].node2] : 0;
+            h_pops[(size_t)cat * c->n_pops + o] = q;
+        }
 
     cudaStream_t s = c->stream;
     CUDA_TRY(c, cudaMemcpyAsync(c->d_keys, h_keys, (size_t)n_keys * sizeof(KeyParams), cudaMemcpyHostToDevice, s));
@@ -381,6 +429,7 @@ int stage_and_build(cafe_b200_ctx* c, const double* lambdas, int n_lambdas, int 
     CUDA_TRY(c, cudaMemcpyAsync(c->d_prior, h_prior, (size_t)c->n * sizeof(double), cudaMemcpyHostToDevice, s));
     CUDA_TRY(c, cudaMemcpyAsync(c->d_logprior, h_logprior, (size_t)c->n * sizeof(double), cudaMemcpyHostToDevice, s));
     CUDA_TRY(c, cudaMemcpyAsync(c->d_catprobs, h_cat, (size_t)k * sizeof(double), cudaMemcpyHostToDevice, s));
+    CUDA_TRY(c, cudaMemcpyAsync(c->d_pops, h_pops, (size_t)k * c->n_pops * sizeof(POp), cudaMemcpyHostToDevice, s));
     CUDA_TRY(c, cudaEventRecord(c->staged, s));
 
     CUDA_TRY(c, cudaEventRecord(c->ev[0], s));
@@ -423,11 +472,11 @@ int launch_prune(cafe_b200_ctx* c, int k, int mode, double* root_out)
     PruneParams p;
     memset(&p, 0, sizeof(p));
     p.n_families = c->n_families; p.n_leaves = c->n_leaves; p.n_nodes = c->tree.n_nodes; p.n_categories = k;
-    p.mf = c->mf; p.mrf = c->mrf; p.n_ops = (int)c->sched.ops.size(); p.n_kchunks = c->n_kchunks; p.mode = mode;
+    p.mf = c->mf; p.mrf = c->mrf; p.n_ops = c->n_pops; p.n_kchunks = c->n_kchunks; p.mode = mode;
     p.rescale = c->rescale; p.n_spill = std::max(1, c->sched.n_spill); p.err_rows = c->err_rows; p.err_ndev = c->err_ndev;
     p.counts_in_smem = (FT * c->n_leaves * 2 <= CNT_CAP_BYTES) ? 1 : 0;
     p.n_slots = c->n_slots; p.n_tiles = c->n_tiles;
-    p.ops = c->d_ops; p.counts = c->d_counts; p.leaf_col = c->d_leaf_col; p.mat_of = c->d_mat_of;
+    p.ops = c->d_pops; p.counts = c->d_counts;
     p.mp = c->d_mp; p.mt = c->d_mt; p.mp_stride = c->mp_stride; p.mt_stride = c->mt_stride;
     p.err = c->d_err; p.prior = c->d_prior; p.logprior = c->d_logprior; p.cat_probs = c->d_catprobs;
     p.scratch = c->d_scratch; p.scratch_exp = c->d_scratch_exp;
@@ -512,6 +561,8 @@ int launch_pupko(cafe_b200_ctx* c, int k, int32_t* states_host)
 int upload_schedule(cafe_b200_ctx* c)
 {
     c->sched = ScheduleBuilder(c->tree, c->n_slots).build();
+    c->fused = fuse_schedule(c->sched.ops, true);
+    if ((int)c->sched.ops.size() > c->pops_cap) c->cap_k = 0;       // force the per-category op buffers to be re-sized
     cudaFree(c->d_ops); cudaFree(c->d_scratch); cudaFree(c->d_scratch_exp);
     c->d_ops = nullptr; c->d_scratch = nullptr; c->d_scratch_exp = nullptr;
     CUDA_TRY(c, dev_alloc(&c->d_ops, c->sched.ops.size()));
@@ -595,6 +646,7 @@ void cafe_b200_destroy(cafe_b200_ctx* c)
     cudaFree(c->d_counts); cudaFree(c->d_ops); cudaFree(c->d_leaf_col); cudaFree(c->d_parent); cudaFree(c->d_child_offset);
     cudaFree(c->d_child_list); cudaFree(c->d_mat_of); cudaFree(c->d_mp); cudaFree(c->d_mt); cudaFree(c->d_keys); cudaFree(c->d_powc);
     cudaFree(c->d_lgamma); cudaFree(c->d_err); cudaFree(c->d_prior); cudaFree(c->d_logprior); cudaFree(c->d_catprobs);
+    cudaFree(c->d_pops);
     cudaFree(c->d_cat_lk); cudaFree(c->d_fail); cudaFree(c->d_family_lnl); cudaFree(c->d_family_fail); cudaFree(c->d_partial);
     cudaFree(c->d_result); cudaFree(c->d_scratch); cudaFree(c->d_scratch_exp);
     if (c->h_stage) cudaFreeHost(c->h_stage);

@@ -35,14 +35,31 @@ enum : int {
     OP_SPILL = 4,      // scratch[b] = V[a]
     OP_FILL = 5,       // V[a] = scratch[b]
     OP_RESCALE = 6,    // per-family power-of-two renormalisation of V[a]
-    OP_ROOT = 7        // root prior / category weight, write results
+    OP_ROOT = 7,       // root prior / category weight, write results
+    // fused forms (pruning kernel only, no error model): same arithmetic, fewer passes over shared memory
+    OP_LEAF_SET2 = 8,      // V[a] = column(leaf node) * column(leaf node2)             (a cherry in one pass)
+    OP_GEMM_SET_LEAF = 9,  // V[a] = (M(node) * V[a]) * column(leaf node2)              (leaf sibling folded into the epilogue)
+    OP_GEMM_MUL_LEAF = 10  // V[a] *= (M(node) * V[b]) * column(leaf node2)
 };
 
+// Tree-level op as the host schedule builder emits it (also what the reconstruction kernel walks).
 struct Op {
     int type;
     int a;
     int b;
     int node;
+};
+
+// Pruning op with everything resolved for one rate category: one aligned 32-byte load per op.
+struct __align__(16) POp {
+    int type;
+    int a;
+    int b;
+    int node;
+    int mat;     // unique-matrix slot of `node`
+    int col;     // count column of `node` when it is a leaf
+    int mat2;    // fused leaf sibling: matrix slot
+    int col2;    //                     count column
 };
 
 struct PruneParams {
@@ -64,10 +81,8 @@ struct PruneParams {
     int n_slots;
     int64_t n_tiles;
     // device pointers
-    const Op* ops;
+    const POp* ops;                 // [k][n_ops]
     const int32_t* counts;          // [F][n_leaves]
-    const int* leaf_col;            // [n_nodes]
-    const int* mat_of;              // [k][n_nodes] -> unique matrix slot
     const double* mp;               // panelised matrices   [U][kpanels][NR][4]
     const double* mt;               // transposed matrices  [U][mf+1][NR]
     size_t mp_stride;               // doubles per matrix

@@ -82,10 +82,11 @@ __global__ void __launch_bounds__(PRUNE_THREADS, 1) prune_kernel(const PrunePara
             uint32_t pos = 0;
             for (int64_t item = blockIdx.x; item < n_items; item += gridDim.x) {
                 const int cat = (int)(item / p.n_tiles);
+                const POp* ops = p.ops + (size_t)cat * p.n_ops;
                 for (int o = 0; o < p.n_ops; ++o) {
-                    const Op op = p.ops[o];
-                    if (op.type != OP_GEMM_SET && op.type != OP_GEMM_MUL) continue;
-                    const double* src = p.mp + (size_t)p.mat_of[cat * p.n_nodes + op.node] * p.mp_stride;
+                    const int type = ops[o].type;
+                    if (type != OP_GEMM_SET && type != OP_GEMM_MUL && type != OP_GEMM_SET_LEAF && type != OP_GEMM_MUL_LEAF) continue;
+                    const double* src = p.mp + (size_t)ops[o].mat * p.mp_stride;
                     for (int ch = 0; ch < p.n_kchunks; ++ch, ++pos) {
                         const uint32_t stage = pos % STAGES;
                         const uint32_t round = pos / STAGES;
@@ -124,14 +125,50 @@ __global__ void __launch_bounds__(PRUNE_THREADS, 1) prune_kernel(const PrunePara
         if (tid < MAX_SLOTS * FT) slot_exp[tid] = 0;
         consumer_sync();
 
+        const POp* ops = p.ops + (size_t)cat * p.n_ops;
+        POp next = ops[0];
         for (int o = 0; o < p.n_ops; ++o) {
-            const Op op = p.ops[o];
+            const POp op = next;
+            if (o + 1 < p.n_ops) next = ops[o + 1];          // prefetch: the load overlaps this op's work
             switch (op.type) {
+            case OP_LEAF_SET2: {
+                // ---- a cherry in one pass: V = column(leaf 1) * column(leaf 2) ----
+                const double* mt1 = p.mt + (size_t)op.mat * p.mt_stride;
+                const double* mt2 = p.mt + (size_t)op.mat2 * p.mt_stride;
+                double* dst = slots + (size_t)op.a * L::SLOT_DOUBLES;
+                double v1[FT / CONSUMER_WARPS][MB], v2[FT / CONSUMER_WARPS][MB];
+                #pragma unroll
+                for (int fi = 0; fi < FT / CONSUMER_WARPS; ++fi) {
+                    const int f = warp * (FT / CONSUMER_WARPS) + fi;
+                    int o1, o2;
+                    if (p.counts_in_smem) { o1 = cnt_s[f * p.n_leaves + op.col]; o2 = cnt_s[f * p.n_leaves + op.col2]; }
+                    else {
+                        int64_t fam = fam0 + f;
+                        if (fam >= p.n_families) fam = p.n_families - 1;
+                        o1 = p.counts[fam * p.n_leaves + op.col]; o2 = p.counts[fam * p.n_leaves + op.col2];
+                    }
+                    #pragma unroll
+                    for (int i = 0; i < MB; ++i) {
+                        v1[fi][i] = __ldg(mt1 + (size_t)o1 * NR + lane + 32 * i);
+                        v2[fi][i] = __ldg(mt2 + (size_t)o2 * NR + lane + 32 * i);
+                    }
+                }
+                #pragma unroll
+                for (int fi = 0; fi < FT / CONSUMER_WARPS; ++fi) {
+                    const int f = warp * (FT / CONSUMER_WARPS) + fi;
+                    double* row = dst + (size_t)f * LDV;
+                    #pragma unroll
+                    for (int i = 0; i < MB; ++i) row[lane + 32 * i] = v1[fi][i] * v2[fi][i];
+                    if (lane == 0) slot_exp[op.a * FT + f] = 0;
+                }
+                consumer_sync();
+                break;
+            }
             case OP_LEAF_SET:
             case OP_LEAF_MUL: {
                 // ---- leaf edge: gather column obs (or an error-model stencil of columns) of M^T ----
-                const double* mt = p.mt + (size_t)p.mat_of[cat * p.n_nodes + op.node] * p.mt_stride;
-                const int col = p.leaf_col[op.node];
+                const double* mt = p.mt + (size_t)op.mat * p.mt_stride;
+                const int col = op.col;
                 double* dst = slots + (size_t)op.a * L::SLOT_DOUBLES;
                 #pragma unroll
                 for (int fi = 0; fi < FT / CONSUMER_WARPS; ++fi) {
@@ -179,14 +216,39 @@ __global__ void __launch_bounds__(PRUNE_THREADS, 1) prune_kernel(const PrunePara
                 break;
             }
             case OP_GEMM_SET:
-            case OP_GEMM_MUL: {
+            case OP_GEMM_MUL:
+            case OP_GEMM_SET_LEAF:
+            case OP_GEMM_MUL_LEAF: {
                 // ---- internal edge: Y = M * V_child on the FP64 tensor pipe ----
-                const int src_slot = (op.type == OP_GEMM_SET) ? op.a : op.b;
+                const bool is_set = (op.type == OP_GEMM_SET || op.type == OP_GEMM_SET_LEAF);
+                const bool with_leaf = (op.type == OP_GEMM_SET_LEAF || op.type == OP_GEMM_MUL_LEAF);
+                const int src_slot = is_set ? op.a : op.b;
                 const double* vsrc = slots + (size_t)src_slot * L::SLOT_DOUBLES + (size_t)(warp_n * 16 + g) * LDV + t4;
                 double acc[MB][2][2];
+                double lf[MB][2][2];       // leaf-sibling factor of each output element (1.0 when there is none)
                 #pragma unroll
                 for (int i = 0; i < MB; ++i) {
                     acc[i][0][0] = acc[i][0][1] = acc[i][1][0] = acc[i][1][1] = 0.0;
+                    lf[i][0][0] = lf[i][0][1] = lf[i][1][0] = lf[i][1][1] = 1.0;
+                }
+                if (with_leaf) {
+                    // issued before the K loop so the L2 latency of the gather hides behind the MMAs
+                    const double* mt2 = p.mt + (size_t)op.mat2 * p.mt_stride + warp_m * 8 * MB + g;
+                    #pragma unroll
+                    for (int nb = 0; nb < 2; ++nb)
+                        #pragma unroll
+                        for (int e = 0; e < 2; ++e) {
+                            const int f = warp_n * 16 + nb * 8 + t4 * 2 + e;
+                            int obs;
+                            if (p.counts_in_smem) obs = cnt_s[f * p.n_leaves + op.col2];
+                            else {
+                                int64_t fam = fam0 + f;
+                                if (fam >= p.n_families) fam = p.n_families - 1;
+                                obs = p.counts[fam * p.n_leaves + op.col2];
+                            }
+                            #pragma unroll
+                            for (int i = 0; i < MB; ++i) lf[i][nb][e] = __ldg(mt2 + (size_t)obs * NR + i * 8);
+                        }
                 }
                 const int a_off = (warp_m * 8 * MB) * 4 + lane;
                 for (int ch = 0; ch < p.n_kchunks; ++ch, ++pos) {
@@ -210,7 +272,7 @@ __global__ void __launch_bounds__(PRUNE_THREADS, 1) prune_kernel(const PrunePara
                     __syncwarp();
                     if (lane == 0) mbar_arrive(&empty_bar[stage]);
                 }
-                consumer_sync();      // every warp is done reading V_child before anyone overwrites it
+                if (is_set) consumer_sync();      // in place: every warp is done reading V_child before anyone overwrites it
                 double* dst = slots + (size_t)op.a * L::SLOT_DOUBLES;
                 #pragma unroll
                 for (int i = 0; i < MB; ++i) {
@@ -220,11 +282,13 @@ __global__ void __launch_bounds__(PRUNE_THREADS, 1) prune_kernel(const PrunePara
                         const int f = warp_n * 16 + nb * 8 + t4 * 2;
                         double* q0 = dst + (size_t)f * LDV + s;
                         double* q1 = q0 + LDV;
-                        if (op.type == OP_GEMM_SET) { *q0 = acc[i][nb][0]; *q1 = acc[i][nb][1]; }
-                        else { *q0 *= acc[i][nb][0]; *q1 *= acc[i][nb][1]; }
+                        const double y0 = acc[i][nb][0] * lf[i][nb][0];
+                        const double y1 = acc[i][nb][1] * lf[i][nb][1];
+                        if (is_set) { *q0 = y0; *q1 = y1; }
+                        else { *q0 *= y0; *q1 *= y1; }
                     }
                 }
-                if (op.type == OP_GEMM_MUL && p.rescale && tid < FT) slot_exp[op.a * FT + tid] += slot_exp[op.b * FT + tid];
+                if (!is_set && p.rescale && tid < FT) slot_exp[op.a * FT + tid] += slot_exp[op.b * FT + tid];
                 consumer_sync();
                 break;
             }
