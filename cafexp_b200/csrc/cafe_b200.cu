@@ -262,6 +262,7 @@ struct cafe_b200_ctx {
     std::vector<FusedOp> fused;         // fused ops: pruning without error model
     int n_slots = 0;
     int hw_slots = 0;
+    int n_stages = 4;                   // pruning ring depth
     int rescale = 0;
     int cap_k = 0;                      // categories the k-dependent buffers are sized for
     size_t mp_stride = 0, mt_stride = 0;
@@ -456,7 +457,7 @@ template <int MB>
 int launch_prune_mb(cafe_b200_ctx* c, const PruneParams& p)
 {
     using L = PruneSmem<MB>;
-    const int smem = L::total_bytes(c->n_slots);
+    const int smem = L::total_bytes(c->n_slots, c->n_stages);
     CUDA_TRY(c, cudaFuncSetAttribute(prune_kernel<MB>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
     const int64_t items = p.n_tiles * p.n_categories;
     const int grid = (int)std::min<int64_t>(items, c->sm_count);
@@ -476,6 +477,7 @@ int launch_prune(cafe_b200_ctx* c, int k, int mode, double* root_out)
     p.rescale = c->rescale; p.n_spill = std::max(1, c->sched.n_spill); p.err_rows = c->err_rows; p.err_ndev = c->err_ndev;
     p.counts_in_smem = (FT * c->n_leaves * 2 <= CNT_CAP_BYTES) ? 1 : 0;
     p.n_slots = c->n_slots; p.n_tiles = c->n_tiles;
+    p.n_stages = c->n_stages; p.stage_shift = c->n_stages == 8 ? 3 : (c->n_stages == 4 ? 2 : 1);
     p.ops = c->d_pops; p.counts = c->d_counts;
     p.mp = c->d_mp; p.mt = c->d_mt; p.mp_stride = c->mp_stride; p.mt_stride = c->mt_stride;
     p.err = c->d_err; p.prior = c->d_prior; p.logprior = c->d_logprior; p.cat_probs = c->d_catprobs;
@@ -720,17 +722,23 @@ int cafe_b200_create(cafe_b200_ctx** out, const cafe_b200_tree* tree, const int3
     CREATE_TRY(cudaEventRecord(c->staged, c->stream));
     for (auto& e : c->ev) CREATE_TRY(cudaEventCreate(&e));
 
-    // shared-memory slots and the schedule
+    // Shared-memory budget: a deep matrix ring matters more than a fourth vector slot (the bulk copies need
+    // ~bandwidth x L2 latency bytes in flight; a spilled vector costs two 40 KB L2 round trips per tile),
+    // so take the deepest ring that still leaves three slots (two as a last resort).
     int slots = 0;
-    switch (c->mb) {
-    case 1: slots = PruneSmem<1>::max_slots(c->smem_optin); break;
-    case 2: slots = PruneSmem<2>::max_slots(c->smem_optin); break;
-    case 3: slots = PruneSmem<3>::max_slots(c->smem_optin); break;
-    case 4: slots = PruneSmem<4>::max_slots(c->smem_optin); break;
-    case 5: slots = PruneSmem<5>::max_slots(c->smem_optin); break;
-    case 6: slots = PruneSmem<6>::max_slots(c->smem_optin); break;
-    case 7: slots = PruneSmem<7>::max_slots(c->smem_optin); break;
-    default: slots = PruneSmem<8>::max_slots(c->smem_optin); break;
+    for (int stages : {8, 4, 2}) {
+        int sl = 0;
+        switch (c->mb) {
+        case 1: sl = PruneSmem<1>::max_slots(c->smem_optin, stages); break;
+        case 2: sl = PruneSmem<2>::max_slots(c->smem_optin, stages); break;
+        case 3: sl = PruneSmem<3>::max_slots(c->smem_optin, stages); break;
+        case 4: sl = PruneSmem<4>::max_slots(c->smem_optin, stages); break;
+        case 5: sl = PruneSmem<5>::max_slots(c->smem_optin, stages); break;
+        case 6: sl = PruneSmem<6>::max_slots(c->smem_optin, stages); break;
+        case 7: sl = PruneSmem<7>::max_slots(c->smem_optin, stages); break;
+        default: sl = PruneSmem<8>::max_slots(c->smem_optin, stages); break;
+        }
+        if (sl >= 3 || (stages == 2 && sl >= 2)) { slots = sl; c->n_stages = stages; break; }
     }
     if (slots < 2) { g_create_error = "not enough shared memory for two vector slots"; cafe_b200_destroy(c); return CAFE_B200_ERR_LIMIT; }
     c->n_slots = c->hw_slots = slots;

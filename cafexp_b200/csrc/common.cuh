@@ -15,7 +15,8 @@ constexpr int FT = 32;                  // families per tile (MMA N dimension = 
 constexpr int CONSUMER_WARPS = 8;       // 4 (rows) x 2 (family columns)
 constexpr int CONSUMER_THREADS = CONSUMER_WARPS * 32;
 constexpr int PRUNE_THREADS = CONSUMER_THREADS + 32;   // + 1 producer warp issuing bulk copies
-constexpr int STAGES = 4;               // ring of matrix K-chunks
+constexpr int STAGES = 4;               // ring of matrix K-chunks (reconstruction kernel)
+constexpr int MAX_STAGES = 8;           // pruning kernel: 2, 4 or 8 stages chosen at create (power of two)
 constexpr int PPS = 2;                  // K panels (of 4 columns) per stage
 constexpr int CNT_CAP_BYTES = 8192;     // staged leaf counts (uint16) per tile, if they fit
 constexpr int LGAMMA_TABLE = 1024;      // src/probability.cpp:52
@@ -79,6 +80,8 @@ struct PruneParams {
     int err_ndev;
     int counts_in_smem;
     int n_slots;
+    int n_stages;           // ring depth (power of two)
+    int stage_shift;        // log2(n_stages)
     int64_t n_tiles;
     // device pointers
     const POp* ops;                 // [k][n_ops]

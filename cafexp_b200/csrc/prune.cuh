@@ -34,15 +34,15 @@ struct PruneSmem {
     static constexpr int LDV = ldv_of(MB);
     static constexpr int STAGE_DOUBLES = stage_doubles(MB);
     static constexpr int STAGE_BYTES = STAGE_DOUBLES * 8;
-    static constexpr int RING_BYTES = STAGES * STAGE_BYTES;
     static constexpr int SLOT_DOUBLES = FT * LDV;
     static constexpr int SLOT_BYTES = SLOT_DOUBLES * 8;
-    static constexpr int MISC_BYTES = 512;     // mbarriers + per-slot exponents
+    static constexpr int MISC_BYTES = 512;     // mbarriers
     static constexpr int EXP_BYTES = MAX_SLOTS * FT * 4;
-    __host__ __device__ static constexpr int total_bytes(int slots) { return RING_BYTES + slots * SLOT_BYTES + CNT_CAP_BYTES + MISC_BYTES + EXP_BYTES; }
-    __host__ static int max_slots(int smem_limit)
+    __host__ __device__ static constexpr int ring_bytes(int stages) { return stages * STAGE_BYTES; }
+    __host__ __device__ static constexpr int total_bytes(int slots, int stages) { return ring_bytes(stages) + slots * SLOT_BYTES + CNT_CAP_BYTES + MISC_BYTES + EXP_BYTES; }
+    __host__ static int max_slots(int smem_limit, int stages)
     {
-        int s = (smem_limit - RING_BYTES - CNT_CAP_BYTES - MISC_BYTES - EXP_BYTES) / SLOT_BYTES;
+        int s = (smem_limit - ring_bytes(stages) - CNT_CAP_BYTES - MISC_BYTES - EXP_BYTES) / SLOT_BYTES;
         return s > MAX_SLOTS ? MAX_SLOTS : s;
     }
 };
@@ -55,18 +55,20 @@ __global__ void __launch_bounds__(PRUNE_THREADS, 1) prune_kernel(const PrunePara
     constexpr int LDV = L::LDV;
     extern __shared__ __align__(128) unsigned char smem_raw[];
     double* ring = reinterpret_cast<double*>(smem_raw);
-    double* slots = reinterpret_cast<double*>(smem_raw + L::RING_BYTES);
-    uint16_t* cnt_s = reinterpret_cast<uint16_t*>(smem_raw + L::RING_BYTES + p.n_slots * L::SLOT_BYTES);
-    uint64_t* full_bar = reinterpret_cast<uint64_t*>(smem_raw + L::RING_BYTES + p.n_slots * L::SLOT_BYTES + CNT_CAP_BYTES);
-    uint64_t* empty_bar = full_bar + STAGES;
-    int* slot_exp = reinterpret_cast<int*>(smem_raw + L::RING_BYTES + p.n_slots * L::SLOT_BYTES + CNT_CAP_BYTES + L::MISC_BYTES);
+    const int ring_bytes = L::ring_bytes(p.n_stages);
+    const uint32_t stage_mask = (uint32_t)p.n_stages - 1u;
+    double* slots = reinterpret_cast<double*>(smem_raw + ring_bytes);
+    uint16_t* cnt_s = reinterpret_cast<uint16_t*>(smem_raw + ring_bytes + p.n_slots * L::SLOT_BYTES);
+    uint64_t* full_bar = reinterpret_cast<uint64_t*>(smem_raw + ring_bytes + p.n_slots * L::SLOT_BYTES + CNT_CAP_BYTES);
+    uint64_t* empty_bar = full_bar + MAX_STAGES;
+    int* slot_exp = reinterpret_cast<int*>(smem_raw + ring_bytes + p.n_slots * L::SLOT_BYTES + CNT_CAP_BYTES + L::MISC_BYTES);
 
     const int tid = threadIdx.x;
     const int warp = tid >> 5;
     const int lane = tid & 31;
 
     if (tid == 0) {
-        for (int s = 0; s < STAGES; ++s) {
+        for (int s = 0; s < p.n_stages; ++s) {
             mbar_init(&full_bar[s], 1);
             mbar_init(&empty_bar[s], CONSUMER_WARPS);
         }
@@ -88,8 +90,8 @@ __global__ void __launch_bounds__(PRUNE_THREADS, 1) prune_kernel(const PrunePara
                     if (type != OP_GEMM_SET && type != OP_GEMM_MUL && type != OP_GEMM_SET_LEAF && type != OP_GEMM_MUL_LEAF) continue;
                     const double* src = p.mp + (size_t)ops[o].mat * p.mp_stride;
                     for (int ch = 0; ch < p.n_kchunks; ++ch, ++pos) {
-                        const uint32_t stage = pos % STAGES;
-                        const uint32_t round = pos / STAGES;
+                        const uint32_t stage = pos & stage_mask;
+                        const uint32_t round = pos >> p.stage_shift;
                         mbar_wait(&empty_bar[stage], (round & 1) ^ 1);
                         mbar_arrive_expect_tx(&full_bar[stage], L::STAGE_BYTES);
                         bulk_copy_g2s(ring + (size_t)stage * L::STAGE_DOUBLES, src + (size_t)ch * L::STAGE_DOUBLES, L::STAGE_BYTES, &full_bar[stage]);
@@ -252,8 +254,8 @@ __global__ void __launch_bounds__(PRUNE_THREADS, 1) prune_kernel(const PrunePara
                 }
                 const int a_off = (warp_m * 8 * MB) * 4 + lane;
                 for (int ch = 0; ch < p.n_kchunks; ++ch, ++pos) {
-                    const uint32_t stage = pos % STAGES;
-                    mbar_wait(&full_bar[stage], (pos / STAGES) & 1);
+                    const uint32_t stage = pos & stage_mask;
+                    mbar_wait(&full_bar[stage], (pos >> p.stage_shift) & 1);
                     const double* a_stage = ring + (size_t)stage * L::STAGE_DOUBLES + a_off;
                     #pragma unroll
                     for (int pp = 0; pp < PPS; ++pp) {
