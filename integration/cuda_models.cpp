@@ -1,0 +1,389 @@
+// CUDA-backed subclasses of the reference's models (see cuda_models.h).  Compiled against the reference's
+// headers; links libcafe_b200.so through the C ABI in include/cafe_b200.h.
+#include "cuda_models.h"
+
+#include <algorithm>
+#include <cmath>
+#include <numeric>
+#include <stdexcept>
+#include <unordered_map>
+
+#include "cafe_b200.h"
+
+#include "clade.h"
+#include "error_model.h"
+#include "gamma.h"
+#include "gene_family.h"
+#include "io.h"
+#include "lambda.h"
+#include "matrix_cache.h"
+#include "root_distribution.h"
+#include "root_equilibrium_distribution.h"
+#include "user_data.h"
+
+namespace {
+
+//! What both reference models do before touching the prior (src/base_model.cpp:62-72, src/gamma_core.cpp:182-192).
+void initialize_prior(root_equilibrium_distribution* prior, const std::map<int, int>& root_distribution_map, int max_root_family_size)
+{
+    root_distribution rd;
+    if (root_distribution_map.size() > 0)
+        rd.vectorize(root_distribution_map);
+    else
+        rd.vectorize_uniform(max_root_family_size);
+    prior->initialize(&rd);
+}
+
+struct count_row_hash {
+    size_t operator()(const std::vector<int>& v) const
+    {
+        size_t h = 1469598103934665603ull;
+        for (int x : v) { h ^= (size_t)x + 0x9e3779b97f4a7c15ull + (h << 6) + (h >> 2); }
+        return h;
+    }
+};
+
+}  // namespace
+
+// ------------------------------------------------------------------------------------------------------
+// cuda_bridge
+// ------------------------------------------------------------------------------------------------------
+
+cuda_bridge::cuda_bridge(const clade* p_tree, int max_family_size, int max_root_family_size)
+    : _p_tree(p_tree), _mf(max_family_size), _mrf(max_root_family_size)
+{
+    p_tree->apply_reverse_level_order([this](const clade* c) { _order.push_back(c); });
+    std::map<const clade*, int> index;
+    for (size_t i = 0; i < _order.size(); ++i) index[_order[i]] = (int)i;
+    const int nn = (int)_order.size();
+    _parent.assign(nn, -1);
+    _leaf_col.assign(nn, -1);
+    _lambda_index.resize(nn);
+    _branch.resize(nn);
+    _child_offset.assign(nn + 1, 0);
+    for (int v = 0; v < nn; ++v) {
+        const clade* c = _order[v];
+        _parent[v] = c->is_root() ? -1 : index.at(c->get_parent());
+        _branch[v] = c->get_branch_length();
+        _lambda_index[v] = v;                       // one lambda slot per node: the value comes from lambda::get_value_for_clade
+        if (c->is_leaf()) {
+            _leaf_col[v] = (int)_leaves.size();
+            _leaves.push_back(c);
+        }
+        else {
+            _internal.push_back(c);
+        }
+        c->apply_to_descendants([&](const clade* d) { _child_list.push_back(index.at(d)); });     // Newick order
+        _child_offset[v + 1] = (int)_child_list.size();
+    }
+}
+
+cuda_bridge::~cuda_bridge()
+{
+    if (_ctx) cafe_b200_destroy(_ctx);
+}
+
+void cuda_bridge::check(int rc, const char* what) const
+{
+    if (rc != CAFE_B200_OK)
+        throw std::runtime_error(std::string(what) + " failed (" + std::to_string(rc) + "): " + cafe_b200_last_error(_ctx));
+}
+
+void cuda_bridge::bind(const std::vector<gene_family>& families)
+{
+    if (_ctx && _bound == &families && _bound_size == families.size()) return;
+    if (_ctx) { cafe_b200_destroy(_ctx); _ctx = nullptr; }
+
+    // Identical count rows are evaluated once.  The reference does this for the base model only
+    // (build_reference_list, src/base_model.cpp:27-51, O(F^2)); identical inputs give identical outputs for
+    // the gamma model as well, so de-duplicating there changes no number.
+    const size_t nl = _leaves.size();
+    std::unordered_map<std::vector<int>, size_t, count_row_hash> seen;
+    std::vector<int32_t> counts;
+    _unique_of.resize(families.size());
+    _max_count = 0;
+    std::vector<int> row(nl);
+    for (size_t i = 0; i < families.size(); ++i) {
+        for (size_t l = 0; l < nl; ++l) row[l] = families[i].get_species_size(_leaves[l]->get_taxon_name());
+        auto it = seen.find(row);
+        if (it == seen.end()) {
+            it = seen.emplace(row, seen.size()).first;
+            counts.insert(counts.end(), row.begin(), row.end());
+            for (int x : row) _max_count = std::max(_max_count, x);
+        }
+        _unique_of[i] = it->second;
+    }
+    _n_unique = seen.size();
+
+    cafe_b200_tree t;
+    t.n_nodes = (int)_order.size();
+    t.parent = _parent.data();
+    t.child_offset = _child_offset.data();
+    t.child_list = _child_list.data();
+    t.leaf_col = _leaf_col.data();
+    t.branch = _branch.data();
+    t.lambda_index = _lambda_index.data();
+    int device = 0;
+    if (const char* e = getenv("CAFE_B200_DEVICE")) device = atoi(e);
+    int rc = cafe_b200_create(&_ctx, &t, counts.data(), (int64_t)_n_unique, (int)nl, _mf, _mrf, device);
+    if (rc != CAFE_B200_OK) {
+        _ctx = nullptr;
+        throw std::runtime_error(std::string("cafe_b200_create failed (") + std::to_string(rc) + "): " + cafe_b200_last_error(nullptr));
+    }
+    _bound = &families;
+    _bound_size = families.size();
+}
+
+void cuda_bridge::set_error_model(const error_model* p_error_model)
+{
+    if (!p_error_model) {
+        check(cafe_b200_set_error_model(_ctx, nullptr, 0, 0), "cafe_b200_set_error_model");
+        return;
+    }
+    // rows for every observed count that occurs: error_model::get_probs(count)  (src/probability.cpp:182)
+    const int nd = (int)p_error_model->n_deviations();
+    const int rows = _max_count + 1;
+    std::vector<double> table((size_t)rows * nd);
+    for (int s = 0; s < rows; ++s) {
+        std::vector<double> probs = p_error_model->get_probs(s);
+        for (int d = 0; d < nd; ++d) table[(size_t)s * nd + d] = probs[d];
+    }
+    check(cafe_b200_set_error_model(_ctx, table.data(), rows, nd), "cafe_b200_set_error_model");
+}
+
+std::vector<double> cuda_bridge::lambda_table(const lambda* p_lambda, const std::vector<double>& multipliers) const
+{
+    const size_t nn = _order.size();
+    std::vector<double> out(multipliers.size() * nn);
+    for (size_t k = 0; k < multipliers.size(); ++k) {
+        std::unique_ptr<lambda> ml(p_lambda->multiply(multipliers[k]));            // src/core.cpp:135
+        for (size_t v = 0; v < nn; ++v)
+            out[k * nn + v] = _order[v]->is_root() ? ml->get_value_for_clade(_order[0]) : ml->get_value_for_clade(_order[v]);
+    }
+    return out;
+}
+
+std::vector<double> cuda_bridge::prior_table(const root_equilibrium_distribution* prior, int n)
+{
+    std::vector<double> out(n);
+    for (int j = 0; j < n; ++j) out[j] = (double)prior->compute(j);
+    return out;
+}
+
+long cuda_bridge::evaluate(const std::vector<double>& lambdas, const std::vector<double>& cat_probs, const std::vector<double>& prior, int mode,
+                           std::vector<double>& family_lnl, std::vector<double>& cat_lk, std::vector<char>& failed)
+{
+    const int k = (int)cat_probs.size();
+    family_lnl.assign(_n_unique, 0.0);
+    cat_lk.assign(mode == CAFE_B200_GAMMA_LINSUM ? _n_unique * k : 0, 0.0);
+    failed.assign(_n_unique, 0);
+    double neg_lnl = 0.0;
+    int64_t n_failed = 0;
+    std::vector<int64_t> failed_idx(_n_unique ? _n_unique : 1);
+    check(cafe_b200_eval(_ctx, lambdas.data(), (int)_order.size(), cat_probs.data(), k, prior.data(), mode, &neg_lnl, family_lnl.data(),
+                         cat_lk.empty() ? nullptr : cat_lk.data(), &n_failed, failed_idx.data(), (int64_t)failed_idx.size()),
+          "cafe_b200_eval");
+    for (int64_t i = 0; i < n_failed; ++i) failed[failed_idx[i]] = 1;
+    return (long)n_failed;
+}
+
+void cuda_bridge::reconstruct(const std::vector<double>& lambdas, int n_categories, const std::vector<double>& prior_by_size, std::vector<int>& states)
+{
+    states.assign(_n_unique * n_categories * _internal.size(), 0);
+    static_assert(sizeof(int) == sizeof(int32_t), "int is 32 bits");
+    check(cafe_b200_reconstruct(_ctx, lambdas.data(), (int)_order.size(), n_categories, prior_by_size.data(), reinterpret_cast<int32_t*>(states.data())),
+          "cafe_b200_reconstruct");
+}
+
+// ------------------------------------------------------------------------------------------------------
+// cuda_base_model
+// ------------------------------------------------------------------------------------------------------
+
+cuda_base_model::cuda_base_model(lambda* p_lambda, const clade* p_tree, const std::vector<gene_family>* p_gene_families, int max_family_size,
+                                 int max_root_family_size, error_model* p_error_model)
+    : base_model(p_lambda, p_tree, p_gene_families, max_family_size, max_root_family_size, p_error_model),
+      _bridge(p_tree, max_family_size, max_root_family_size)
+{
+}
+
+double cuda_base_model::infer_family_likelihoods(root_equilibrium_distribution* prior, const std::map<int, int>& root_distribution_map, const lambda* p_lambda)
+{
+    _monitor.Event_InferenceAttempt_Started();
+    if (!_p_lambda->is_valid()) {                                                   // src/base_model.cpp:56-60
+        _monitor.Event_InferenceAttempt_InvalidValues();
+        return -log(0);
+    }
+    initialize_prior(prior, root_distribution_map, _max_root_family_size);
+
+    _bridge.bind(*_p_gene_families);
+    _bridge.set_error_model(_p_error_model);                                       // the epsilon optimiser edits it in place between calls
+    std::vector<double> family_lnl, cat_lk;
+    std::vector<char> failed;
+    _bridge.evaluate(_bridge.lambda_table(_p_lambda, {1.0}), {1.0}, cuda_bridge::prior_table(prior, _max_root_family_size),
+                     CAFE_B200_BASE_LOGMAX, family_lnl, cat_lk, failed);
+
+    const size_t F = _p_gene_families->size();
+    results.resize(F);
+    std::vector<double> all_families_likelihood(F);
+    for (size_t i = 0; i < F; ++i) {
+        all_families_likelihood[i] = family_lnl[_bridge.unique_of(i)];
+        results[i] = family_info_stash(_p_gene_families->at(i).id(), 0.0, 0.0, 0.0, all_families_likelihood[i], false);
+    }
+    // summed on the host in family order, as the reference does (src/base_model.cpp:107)
+    double final_likelihood = -std::accumulate(all_families_likelihood.begin(), all_families_likelihood.end(), 0.0);
+    _monitor.Event_InferenceAttempt_Complete(final_likelihood);
+    return final_likelihood;
+}
+
+reconstruction* cuda_base_model::reconstruct_ancestral_states(const std::vector<gene_family>& families, matrix_cache* p_calc, root_equilibrium_distribution* p_prior)
+{
+    _monitor.Event_Reconstruction_Started("Base");
+    auto result = new base_model_reconstruction();
+    // callers read transition matrices from *p_calc afterwards (compute_viterbi_sum, src/execute.cpp:158-170)
+    p_calc->precalculate_matrices(get_lambda_values(_p_lambda), _p_tree->get_branch_lengths());
+
+    _bridge.bind(families);
+    const int lim = std::min(_max_family_size, _max_root_family_size) + 1;         // src/gene_family_reconstructor.cpp:41-56
+    std::vector<int> states;
+    _bridge.reconstruct(_bridge.lambda_table(_p_lambda, {1.0}), 1, cuda_bridge::prior_table(p_prior, lim), states);
+    const auto& internal = _bridge.internal_nodes();
+    for (size_t i = 0; i < families.size(); ++i) {
+        clademap<int>& r = result->_reconstructions[families[i].id()];
+        const int* row = &states[_bridge.unique_of(i) * internal.size()];
+        for (size_t n = 0; n < internal.size(); ++n) r[internal[n]] = row[n];
+    }
+    _monitor.Event_Reconstruction_Complete();
+    return result;
+}
+
+// ------------------------------------------------------------------------------------------------------
+// cuda_gamma_model
+// ------------------------------------------------------------------------------------------------------
+
+cuda_gamma_model::cuda_gamma_model(lambda* p_lambda, clade* p_tree, std::vector<gene_family>* p_gene_families, int max_family_size,
+                                   int max_root_family_size, int n_gamma_cats, double fixed_alpha, error_model* p_error_model)
+    : gamma_model(p_lambda, p_tree, p_gene_families, max_family_size, max_root_family_size, n_gamma_cats, fixed_alpha, p_error_model),
+      _bridge(p_tree, max_family_size, max_root_family_size), _explicit_categories(false)
+{
+}
+
+cuda_gamma_model::cuda_gamma_model(lambda* p_lambda, clade* p_tree, std::vector<gene_family>* p_gene_families, int max_family_size,
+                                   int max_root_family_size, std::vector<double> gamma_categories, std::vector<double> multipliers,
+                                   error_model* p_error_model)
+    : gamma_model(p_lambda, p_tree, p_gene_families, max_family_size, max_root_family_size, gamma_categories, multipliers, p_error_model),
+      _bridge(p_tree, max_family_size, max_root_family_size), _explicit_categories(true), _explicit_cat_probs(gamma_categories)
+{
+}
+
+std::vector<double> cuda_gamma_model::cat_probs() const
+{
+    if (_explicit_categories) return _explicit_cat_probs;
+    // gamma_model keeps _gamma_cat_probs private; they are a pure function of (k, alpha): src/gamma_core.cpp:58-64
+    const size_t k = get_gamma_cat_probs_count();
+    std::vector<double> freq(k), rate(k);
+    if (k > 1) get_gamma(freq, rate, get_alpha());
+    return freq;
+}
+
+double cuda_gamma_model::infer_family_likelihoods(root_equilibrium_distribution* prior, const std::map<int, int>& root_distribution_map, const lambda* p_lambda)
+{
+    _monitor.Event_InferenceAttempt_Started();
+    results.clear();
+    if (!can_infer()) {                                                             // src/gamma_core.cpp:175-179
+        _monitor.Event_InferenceAttempt_InvalidValues();
+        return -log(0);
+    }
+    initialize_prior(prior, root_distribution_map, _max_root_family_size);
+
+    const std::vector<double> multipliers = get_lambda_multipliers();
+    const std::vector<double> probs = cat_probs();
+    const size_t k = probs.size();
+    _bridge.bind(*_p_gene_families);
+    _bridge.set_error_model(_p_error_model);
+    std::vector<double> family_lnl, cat_lk;
+    std::vector<char> failed;
+    const long n_failed = _bridge.evaluate(_bridge.lambda_table(p_lambda, multipliers), probs, cuda_bridge::prior_table(prior, _max_root_family_size),
+                                           CAFE_B200_GAMMA_LINSUM, family_lnl, cat_lk, failed);
+
+    const size_t F = _p_gene_families->size();
+    _cat_lk.assign(F, std::vector<double>());
+    if (n_failed > 0) {                                                             // src/gamma_core.cpp:227-236
+        for (size_t i = 0; i < F; ++i)
+            if (failed[_bridge.unique_of(i)]) _monitor.Event_InferenceAttempt_Saturation(_p_gene_families->at(i).id());
+        return -log(0);
+    }
+    std::vector<double> all_bundles_likelihood(F);
+    for (size_t i = 0; i < F; ++i) {
+        const double* cl = &cat_lk[_bridge.unique_of(i) * k];
+        _cat_lk[i].assign(cl, cl + k);
+        const double family_likelihood = std::accumulate(cl, cl + k, 0.0);         // src/gamma_core.cpp:207
+        // posterior: the reference multiplies by the category probability a second time (src/gamma_core.cpp:97-109)
+        double denominator = 0.0;
+        for (size_t c = 0; c < k; ++c) denominator += cl[c] * probs[c];
+        for (size_t c = 0; c < k; ++c) {
+            const double posterior = cl[c] * probs[c] / denominator;
+            results.push_back(family_info_stash(_p_gene_families->at(i).id(), multipliers[c], cl[c], family_likelihood, posterior, posterior > 0.95));
+        }
+        all_bundles_likelihood[i] = std::log(family_likelihood);
+    }
+    double final_likelihood = -std::accumulate(all_bundles_likelihood.begin(), all_bundles_likelihood.end(), 0.0);
+    _monitor.Event_InferenceAttempt_Complete(final_likelihood);
+    return final_likelihood;
+}
+
+reconstruction* cuda_gamma_model::reconstruct_ancestral_states(const std::vector<gene_family>& families, matrix_cache* p_calc, root_equilibrium_distribution* p_prior)
+{
+    _monitor.Event_Reconstruction_Started("Gamma");
+    const std::vector<double> multipliers = get_lambda_multipliers();
+    const std::vector<double> probs = cat_probs();
+    const size_t k = multipliers.size();
+
+    std::vector<double> all;                                                        // src/gamma_core.cpp:305-315
+    for (double multiplier : multipliers)
+        for (double lam : get_lambda_values(_p_lambda)) all.push_back(lam * multiplier);
+    p_calc->precalculate_matrices(all, _p_tree->get_branch_lengths());
+
+    _bridge.bind(families);
+    const int lim = std::min(_max_family_size, _max_root_family_size) + 1;
+    std::vector<int> states;
+    _bridge.reconstruct(_bridge.lambda_table(_p_lambda, multipliers), (int)k, cuda_bridge::prior_table(p_prior, lim), states);
+
+    gamma_model_reconstruction* result = new gamma_model_reconstruction(multipliers);
+    const auto& internal = _bridge.internal_nodes();
+    for (size_t i = 0; i < families.size(); ++i) {
+        auto& rec = result->_reconstructions[families[i].id()];
+        if (i < _cat_lk.size()) rec._category_likelihoods = _cat_lk[i];
+        rec.category_reconstruction.resize(k);
+        const int* row = &states[_bridge.unique_of(i) * k * internal.size()];
+        for (size_t c = 0; c < k; ++c)
+            for (size_t n = 0; n < internal.size(); ++n) rec.category_reconstruction[c][internal[n]] = row[c * internal.size() + n];
+        rec.reconstruction = get_weighted_averages(rec.category_reconstruction, probs);   // src/gamma_core.cpp:338-342
+    }
+    _monitor.Event_Reconstruction_Complete();
+    return result;
+}
+
+// ------------------------------------------------------------------------------------------------------
+
+std::vector<model*> build_cuda_models(const input_parameters& user_input, user_data& user_data)
+{
+    model* p_model = NULL;
+    std::vector<gene_family>* p_gene_families = &user_data.gene_families;
+    if (user_input.is_simulating) p_gene_families = NULL;
+
+    if (user_input.fixed_alpha > 0 || user_input.n_gamma_cats > 1) {
+        p_model = new cuda_gamma_model(user_data.p_lambda, user_data.p_tree, &user_data.gene_families, user_data.max_family_size,
+                                       user_data.max_root_family_size, user_input.n_gamma_cats, user_input.fixed_alpha, user_data.p_error_model);
+    }
+    else {
+        error_model* p_error_model = user_data.p_error_model;
+        if (user_input.use_error_model && !p_error_model) {                         // src/core.cpp:37-42
+            p_error_model = new error_model();
+            p_error_model->set_probabilities(0, {0, .95, 0.05});
+            p_error_model->set_probabilities(user_data.max_family_size, {0.05, .9, 0.05});
+        }
+        p_model = new cuda_base_model(user_data.p_lambda, user_data.p_tree, p_gene_families, user_data.max_family_size,
+                                      user_data.max_root_family_size, p_error_model);
+    }
+    return std::vector<model*>{p_model};
+}

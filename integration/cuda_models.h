@@ -1,0 +1,133 @@
+// Reference-side binding of libcafe_b200.so: CUDA-backed subclasses of the reference's own models.
+//
+// This file is compiled INSIDE the reference's source tree (it includes the reference's headers; it holds
+// none of the reference's code).  It is what a CAFExp maintainer adds to route the likelihood hot path to
+// the B200 engine:
+//
+//      base_model  -> cuda_base_model      overrides infer_family_likelihoods      (src/base_model.cpp:53-112)
+//                                                    reconstruct_ancestral_states  (src/base_model.cpp:145-162)
+//      gamma_model -> cuda_gamma_model     overrides infer_family_likelihoods      (src/gamma_core.cpp:169-248)
+//                                                    reconstruct_ancestral_states  (src/gamma_core.cpp:301-347)
+//      build_models -> build_cuda_models   the single construction site            (src/core.cpp:16-50)
+//
+// Everything else — optimizer, scorers, lambda containers, error-model bookkeeping, discrete-gamma
+// multipliers, report writers — is the reference's unchanged host code and keeps calling the same
+// virtuals (optimizer_scorer::calculate_score -> model::infer_family_likelihoods, src/optimizer_scorer.cpp:19-33).
+// There is no CPU fallback: if the CUDA library reports an error the overrides throw std::runtime_error,
+// which cafexp() already catches (src/cafexp.cpp:215-218).
+#ifndef CAFE_B200_CUDA_MODELS_H
+#define CAFE_B200_CUDA_MODELS_H
+
+#include <map>
+#include <memory>
+#include <string>
+#include <vector>
+
+#include "base_model.h"
+// src/gamma_core.h has no include guard; a translation unit that already included it defines this macro first
+#ifndef CAFEXP_GAMMA_CORE_H_INCLUDED
+#define CAFEXP_GAMMA_CORE_H_INCLUDED
+#include "gamma_core.h"
+#endif
+
+struct cafe_b200_ctx;
+class clade;
+class gene_family;
+class lambda;
+class error_model;
+class root_equilibrium_distribution;
+
+//! Flattened (tree, de-duplicated families) and the device context that holds them.
+//! One bridge per model object; it is rebuilt when the family vector it was built for changes.
+class cuda_bridge {
+public:
+    cuda_bridge(const clade* p_tree, int max_family_size, int max_root_family_size);
+    ~cuda_bridge();
+    cuda_bridge(const cuda_bridge&) = delete;
+    cuda_bridge& operator=(const cuda_bridge&) = delete;
+
+    //! (Re)creates the device context if `families` is not the vector the current one was built from.
+    void bind(const std::vector<gene_family>& families);
+
+    //! Uploads the error model as a dense [observed count][deviation] table (or removes it).
+    void set_error_model(const error_model* p_error_model);
+
+    //! lambdas[k][node] = (p_lambda * multiplier_k)->get_value_for_clade(node)   (src/lambda.h:45-48,76-84)
+    std::vector<double> lambda_table(const lambda* p_lambda, const std::vector<double>& multipliers) const;
+
+    //! prior[j] = (double)prior->compute(j), j = 0..n-1   (a float widened, src/root_equilibrium_distribution.h:15)
+    static std::vector<double> prior_table(const root_equilibrium_distribution* prior, int n);
+
+    //! One evaluation on the device.  Outputs are per UNIQUE family; expand with unique_of().
+    //! Returns the number of unique families whose pruning failed (gamma mode).
+    long evaluate(const std::vector<double>& lambdas, const std::vector<double>& cat_probs, const std::vector<double>& prior, int mode,
+                  std::vector<double>& family_lnl, std::vector<double>& cat_lk, std::vector<char>& failed);
+
+    //! Pupko reconstruction on the device: states[unique family][category][internal node].
+    void reconstruct(const std::vector<double>& lambdas, int n_categories, const std::vector<double>& prior_by_size, std::vector<int>& states);
+
+    size_t unique_of(size_t family_index) const { return _unique_of[family_index]; }
+    size_t unique_count() const { return _n_unique; }
+    int node_count() const { return (int)_order.size(); }
+    const std::vector<const clade*>& internal_nodes() const { return _internal; }
+    int max_family_size() const { return _mf; }
+    int max_root_family_size() const { return _mrf; }
+
+private:
+    const clade* _p_tree;
+    int _mf, _mrf;
+    std::vector<const clade*> _order;       // apply_reverse_level_order (src/clade.cpp:255-280)
+    std::vector<const clade*> _internal;    // internal nodes in that order, root last
+    std::vector<const clade*> _leaves;      // leaf nodes in that order = count-matrix columns
+    std::vector<int> _parent, _child_offset, _child_list, _leaf_col, _lambda_index;
+    std::vector<double> _branch;
+    const std::vector<gene_family>* _bound = nullptr;
+    size_t _bound_size = 0;
+    std::vector<size_t> _unique_of;
+    size_t _n_unique = 0;
+    int _max_count = 0;
+    cafe_b200_ctx* _ctx = nullptr;
+
+    void check(int rc, const char* what) const;
+};
+
+class cuda_base_model : public base_model {
+public:
+    cuda_base_model(lambda* p_lambda, const clade* p_tree, const std::vector<gene_family>* p_gene_families, int max_family_size,
+                    int max_root_family_size, error_model* p_error_model);
+
+    double infer_family_likelihoods(root_equilibrium_distribution* prior, const std::map<int, int>& root_distribution_map, const lambda* p_lambda) override;
+    reconstruction* reconstruct_ancestral_states(const std::vector<gene_family>& families, matrix_cache* p_calc, root_equilibrium_distribution* p_prior) override;
+    std::string name() const override { return "Base"; }
+
+private:
+    cuda_bridge _bridge;
+};
+
+class cuda_gamma_model : public gamma_model {
+public:
+    cuda_gamma_model(lambda* p_lambda, clade* p_tree, std::vector<gene_family>* p_gene_families, int max_family_size, int max_root_family_size,
+                     int n_gamma_cats, double fixed_alpha, error_model* p_error_model);
+    cuda_gamma_model(lambda* p_lambda, clade* p_tree, std::vector<gene_family>* p_gene_families, int max_family_size, int max_root_family_size,
+                     std::vector<double> gamma_categories, std::vector<double> multipliers, error_model* p_error_model);
+
+    double infer_family_likelihoods(root_equilibrium_distribution* prior, const std::map<int, int>& root_distribution_map, const lambda* p_lambda) override;
+    reconstruction* reconstruct_ancestral_states(const std::vector<gene_family>& families, matrix_cache* p_calc, root_equilibrium_distribution* p_prior) override;
+    std::string name() const override { return "Gamma"; }
+
+    //! category likelihoods of the last evaluation, per family (the reference keeps these private)
+    const std::vector<std::vector<double>>& category_likelihoods() const { return _cat_lk; }
+
+private:
+    cuda_bridge _bridge;
+    bool _explicit_categories;
+    std::vector<double> _explicit_cat_probs;
+    std::vector<std::vector<double>> _cat_lk;
+
+    std::vector<double> cat_probs() const;
+};
+
+//! Same decisions as build_models (src/core.cpp:16-50), instantiating the CUDA-backed subclasses.
+std::vector<model*> build_cuda_models(const input_parameters& user_input, user_data& user_data);
+
+#endif

@@ -52,6 +52,7 @@
 #include "core.h"
 #include "base_model.h"
 #include "gamma_core.h"
+#define CAFEXP_GAMMA_CORE_H_INCLUDED
 #include "gamma.h"
 #include "lambda.h"
 #include "matrix_cache.h"
@@ -66,6 +67,12 @@
 #include "gene_family_reconstructor.h"
 #undef private
 #undef protected
+#ifdef WITH_CUDA_MODELS
+// Second build of this driver (oracle/_ref/ref_harness_cuda): the same unmodified reference host code —
+// optimizer, scorers, readers — with the model objects swapped for the CUDA-backed subclasses of
+// integration/cuda_models.cpp when --cuda 1 is given.  Used by the GPU tests for fit parity.
+#include "cuda_models.h"
+#endif
 
 std::mt19937 randomizer_engine(10);   // the reference's main.cpp defines this global; we replace main.cpp
 
@@ -130,7 +137,7 @@ struct setup {
         in.tree_file_path = a.str("tree");
         in.input_file_path = a.str("fam");
         in.error_model_file_path = a.str("err");
-        in.use_error_model = a.has("err");
+        in.use_error_model = a.has("err") || a.integer("esterr", 0) != 0;      // --esterr 1: "-e" without a file => epsilon is estimated
         in.lambda_tree_file_path = a.str("ltree");
         in.rootdist = a.str("rootdist");
         in.n_gamma_cats = (int)a.integer("k", 1);
@@ -155,7 +162,12 @@ struct setup {
         long limit = a.integer("limit", -1);
         if (limit >= 0 && (size_t)limit < data.gene_families.size()) data.gene_families.resize(limit);
         data.p_prior.reset(root_eq_dist_factory(in, &data.gene_families));
+#ifdef WITH_CUDA_MODELS
+        models = a.integer("cuda", 0) ? build_cuda_models(in, data) : build_models(in, data);
+#else
+        if (a.integer("cuda", 0)) throw std::runtime_error("--cuda needs the ref_harness_cuda build");
         models = build_models(in, data);
+#endif
 
         data.p_tree->apply_reverse_level_order([this](const clade* c) { order.push_back(c); if (!c->is_leaf()) internal.push_back(c); });
     }
@@ -274,7 +286,11 @@ int cmd_eval(const args_t& a)
         // dump layout: F x k category likelihoods (as left in _category_likelihoods, possibly truncated on failure)
         size_t k = gm->_gamma_cat_probs.size();
         std::vector<double> flat(F * k, std::nan(""));
-        for (size_t i = 0; i < F; ++i) for (size_t j = 0; j < gm->_category_likelihoods[i].size() && j < k; ++j) flat[i * k + j] = gm->_category_likelihoods[i][j];
+        const std::vector<std::vector<double>>* cl = &gm->_category_likelihoods;
+#ifdef WITH_CUDA_MODELS
+        if (auto cg = dynamic_cast<cuda_gamma_model*>(m)) cl = &cg->category_likelihoods();
+#endif
+        for (size_t i = 0; i < F && i < cl->size(); ++i) for (size_t j = 0; j < (*cl)[i].size() && j < k; ++j) flat[i * k + j] = (*cl)[i][j];
         d.doubles(flat.data(), flat.size());
     }
     else {

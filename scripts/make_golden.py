@@ -231,6 +231,7 @@ def fits():
         "single_lambda_seed10": dict(seed=10),
         "lambda_epsilon_seed10": dict(seed=10, err=os.path.join(EX, "errormodel_0.1.txt")),
         "two_lambda_seed10": dict(seed=10, ltree=os.path.join(EX, "chimphuman_separate_lambda.txt")),
+        "lambda_estimated_epsilon_seed10": dict(seed=10, esterr=1),
         "gamma4_lambda_alpha_seed10": dict(seed=10, k=4),
     }
     for name, kw in jobs.items():
