@@ -239,7 +239,7 @@ def main():
     dev = torch.device("cuda", local)
 
     F = args.families
-    first, last = rank * F // world, (rank + 1) * F // world
+    first, last = rank * F // world, (rank + 1) * F // world          # == sharded.shard_range(F, rank, world)
     t_gen = time.time()
     tree, counts, newick = synth.config5(F, N_LEAVES, SEED, LAMBDA, first=first, last=last)
     t_gen = time.time() - t_gen
@@ -256,10 +256,11 @@ def main():
     result = torch.zeros(2, dtype=torch.float64, device=dev)
     flush = torch.empty(256 * 1024 * 1024, dtype=torch.uint8, device=dev)
 
+    from cafexp_b200 import sharded
+    job = sharded.ShardedLikelihood(sharded.engine_local_eval(eng), result)     # shard evaluation + one 2-double allreduce
+
     def step():
-        eng.infer_device(lams, prior, freq, engine.GAMMA_LINSUM, result.data_ptr())
-        if world > 1:
-            dist.all_reduce(result)
+        job.enqueue(lams, prior, freq, engine.GAMMA_LINSUM)
 
     def barrier():
         if world > 1:
