@@ -1,0 +1,41 @@
+#!/usr/bin/env python
+"""Small driver for ncu: one config-5-shaped evaluation (+ optional reconstruction) so every kernel launches once or twice.
+
+    ncu --set full --import-source on -k regex:prune_kernel -c 1 python scripts/profile_run.py --families 131072
+"""
+import argparse
+import os
+import sys
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+sys.path.insert(0, ROOT)
+
+from cafexp_b200 import engine, synth  # noqa: E402
+import bench  # noqa: E402
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--families", type=int, default=131072)
+    ap.add_argument("--evals", type=int, default=2)
+    ap.add_argument("--recon", type=int, default=0, help="families to reconstruct (0 = skip)")
+    args = ap.parse_args()
+    tree, counts, _ = synth.config5(args.families, bench.N_LEAVES, bench.SEED, bench.LAMBDA, first=0, last=args.families)
+    freq, rate, prior = bench.gamma_parameters()
+    lams = np.ascontiguousarray(rate[:, None] * np.array([[bench.LAMBDA]]))
+    with engine.Engine(tree, counts, bench.MF, bench.MRF) as eng:
+        for _ in range(args.evals):
+            res = eng.infer(lams, prior, freq, engine.GAMMA_LINSUM, want_family=False, want_cat=False)
+        print("score", res["score"], eng.last_timings_ms())
+    if args.recon:
+        from oracle import binding as orc
+        prior_sz = orc.prior_uniform(bench.MRF, None, min(bench.MF, bench.MRF) + 1)
+        with engine.Engine(tree, counts[: args.recon], bench.MF, bench.MRF) as eng:
+            eng.reconstruct(lams, prior_sz)
+            print("reconstruct", eng.last_timings_ms())
+
+
+if __name__ == "__main__":
+    main()
