@@ -82,6 +82,8 @@ struct PruneParams {
     int n_slots;
     int n_stages;           // ring depth (power of two)
     int stage_shift;        // log2(n_stages)
+    int ops_in_smem;        // per-group copies of the op list live in shared memory
+    int lag_chunks;         // ring stages by which consumer group 1 trails group 0 (0 = no stagger)
     int64_t n_tiles;
     // device pointers
     const POp* ops;                 // [k][n_ops]

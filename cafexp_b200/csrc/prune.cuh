@@ -14,11 +14,19 @@
 // tile of FT=32 families of one rate category.  Partial-likelihood vectors never leave the SM:
 // they sit in shared-memory slots V[family][size].  An internal edge is the dense FP64 contraction
 //      Y[NR x FT] = M_edge[NR x K] * V_child[K x FT]
-// issued as mma.sync.m8n8k4.f64 (DMMA) by 8 consumer warps (4 row groups x 2 family groups, 40x16
-// outputs per warp for NR=160), accumulators in registers for the whole K loop.  The matrix streams
-// from L2 through a 4-stage shared-memory ring filled by 1-D bulk async copies (TMA engine,
-// cp.async.bulk + mbarrier complete_tx) issued by a dedicated producer warp that runs ahead across
-// ops, so the next edge's first chunks land while the consumers do leaf gathers or the epilogue.
+// issued as mma.sync.m8n8k4.f64 (DMMA), accumulators in registers for the whole K loop.  The matrix
+// streams from L2 through a shared-memory ring filled by 1-D bulk async copies (TMA engine,
+// cp.async.bulk + mbarrier complete_tx) issued by a dedicated producer warp that runs ahead across ops.
+//
+// The 8 consumer warps form TWO INDEPENDENT GROUPS of 4 warps; group g owns families [16g, 16g+16) of
+// the tile (its half of every slot), has its own named barrier, and walks the same op list, so both
+// groups consume the SAME matrix stream from the shared ring (a stage is released when all 8 warps
+// have read it) — L2 traffic per flop is that of a 32-family tile.  Group 1 starts LAG chunks behind
+// group 0 and the offset persists, so while one group is between GEMMs (epilogue, child product, leaf
+// gathers, barriers) the other keeps the FP64 tensor pipe busy; each SM sub-partition hosts one warp of
+// each group.  Inside a GEMM the A/B fragments are double-buffered in registers across ring stages, so
+// a warp running alone can still issue DMMAs back to back.
+//
 // The epilogue multiplies the product straight into the parent's accumulator slot (child product);
 // leaf edges are gathers of one matrix column (or an error-model stencil of columns), not GEMMs.
 // HBM traffic per family is just its leaf counts in and k+1 doubles out.
@@ -27,6 +35,12 @@
 #include "common.cuh"
 
 namespace cafe {
+
+constexpr int GROUPS = 2;
+constexpr int GROUP_WARPS = CONSUMER_WARPS / GROUPS;     // 4: one per SM sub-partition
+constexpr int GROUP_THREADS = GROUP_WARPS * 32;
+constexpr int GFT = FT / GROUPS;                         // 16 families per group = 2 n8 blocks
+constexpr int FPW = GFT / GROUP_WARPS;                   // 4 families per warp in the gather / root ops
 
 template <int MB>
 struct PruneSmem {
@@ -39,13 +53,20 @@ struct PruneSmem {
     static constexpr int MISC_BYTES = 512;     // mbarriers
     static constexpr int EXP_BYTES = MAX_SLOTS * FT * 4;
     __host__ __device__ static constexpr int ring_bytes(int stages) { return stages * STAGE_BYTES; }
-    __host__ __device__ static constexpr int total_bytes(int slots, int stages) { return ring_bytes(stages) + slots * SLOT_BYTES + CNT_CAP_BYTES + MISC_BYTES + EXP_BYTES; }
+    __host__ __device__ static constexpr int fixed_bytes(int slots, int stages) { return ring_bytes(stages) + slots * SLOT_BYTES + CNT_CAP_BYTES + MISC_BYTES + EXP_BYTES; }
+    // ops_bytes: per-group copies of the resolved op list (0 = read the ops from global memory)
+    __host__ __device__ static constexpr int total_bytes(int slots, int stages, int ops_bytes) { return fixed_bytes(slots, stages) + ops_bytes; }
     __host__ static int max_slots(int smem_limit, int stages)
     {
         int s = (smem_limit - ring_bytes(stages) - CNT_CAP_BYTES - MISC_BYTES - EXP_BYTES) / SLOT_BYTES;
         return s > MAX_SLOTS ? MAX_SLOTS : s;
     }
 };
+
+__device__ __forceinline__ void group_sync(int group)
+{
+    asm volatile("bar.sync %0, %1;" ::"r"(group + 1), "n"(GROUP_THREADS) : "memory");
+}
 
 template <int MB>
 __global__ void __launch_bounds__(PRUNE_THREADS, 1) prune_kernel(const PruneParams p)
@@ -61,7 +82,9 @@ __global__ void __launch_bounds__(PRUNE_THREADS, 1) prune_kernel(const PrunePara
     uint16_t* cnt_s = reinterpret_cast<uint16_t*>(smem_raw + ring_bytes + p.n_slots * L::SLOT_BYTES);
     uint64_t* full_bar = reinterpret_cast<uint64_t*>(smem_raw + ring_bytes + p.n_slots * L::SLOT_BYTES + CNT_CAP_BYTES);
     uint64_t* empty_bar = full_bar + MAX_STAGES;
+    uint64_t* lag_bar = empty_bar + MAX_STAGES;
     int* slot_exp = reinterpret_cast<int*>(smem_raw + ring_bytes + p.n_slots * L::SLOT_BYTES + CNT_CAP_BYTES + L::MISC_BYTES);
+    POp* ops_s = reinterpret_cast<POp*>(smem_raw + L::fixed_bytes(p.n_slots, p.n_stages));
 
     const int tid = threadIdx.x;
     const int warp = tid >> 5;
@@ -72,6 +95,7 @@ __global__ void __launch_bounds__(PRUNE_THREADS, 1) prune_kernel(const PrunePara
             mbar_init(&full_bar[s], 1);
             mbar_init(&empty_bar[s], CONSUMER_WARPS);
         }
+        mbar_init(lag_bar, GROUP_WARPS);
         fence_barrier_init();
     }
     __syncthreads();
@@ -103,47 +127,59 @@ __global__ void __launch_bounds__(PRUNE_THREADS, 1) prune_kernel(const PrunePara
     }
 
     // =============================== consumers =====================================================
-    const int warp_m = warp & 3;          // row group: rows [warp_m*8*MB, +8*MB)
-    const int warp_n = warp >> 2;         // family group: columns [warp_n*16, +16)
-    const int g = lane >> 2;              // fragment row / column group
+    const int group = warp / GROUP_WARPS;         // family half of the tile: columns [group*16, +16)
+    const int wg = warp % GROUP_WARPS;            // row group: rows [wg*8*MB, +8*MB)
+    const int gtid = tid - group * GROUP_THREADS; // thread index inside the group
+    const int g = lane >> 2;                      // fragment row / column group
     const int t4 = lane & 3;
+    const int fbase = group * GFT;                // first tile family of this group
     uint32_t pos = 0;
+    bool lag_pending = (p.lag_chunks > 0);        // group 0 signals once, group 1 waits once
+    int ops_cat = -1;
+    POp* my_ops = ops_s + (size_t)group * p.n_ops;
+    uint16_t* my_cnt = cnt_s + (size_t)fbase * p.n_leaves;
 
     for (int64_t item = blockIdx.x; item < n_items; item += gridDim.x) {
         const int cat = (int)(item / p.n_tiles);
         const int64_t tile = item % p.n_tiles;
-        const int64_t fam0 = tile * FT;
+        const int64_t fam0 = tile * FT + fbase;   // first family of this group
 
-        consumer_sync();      // previous item fully finished with shared memory
+        group_sync(group);      // previous item fully finished with this group's shared memory
         if (p.counts_in_smem) {
-            const int total = FT * p.n_leaves;
-            for (int i = tid; i < total; i += CONSUMER_THREADS) {
+            const int total = GFT * p.n_leaves;
+            for (int i = gtid; i < total; i += GROUP_THREADS) {
                 const int f = i / p.n_leaves;
                 int64_t fam = fam0 + f;
                 if (fam >= p.n_families) fam = p.n_families - 1;
-                cnt_s[i] = (uint16_t)p.counts[fam * p.n_leaves + (i - f * p.n_leaves)];
+                my_cnt[i] = (uint16_t)p.counts[fam * p.n_leaves + (i - f * p.n_leaves)];
             }
         }
-        if (tid < MAX_SLOTS * FT) slot_exp[tid] = 0;
-        consumer_sync();
+        if (p.ops_in_smem && cat != ops_cat) {
+            const int4* src = reinterpret_cast<const int4*>(p.ops + (size_t)cat * p.n_ops);
+            int4* dst = reinterpret_cast<int4*>(my_ops);
+            for (int i = gtid; i < 2 * p.n_ops; i += GROUP_THREADS) dst[i] = src[i];
+            ops_cat = cat;
+        }
+        if (gtid < MAX_SLOTS * GFT) slot_exp[(gtid / GFT) * FT + fbase + (gtid % GFT)] = 0;
+        group_sync(group);
 
-        const POp* ops = p.ops + (size_t)cat * p.n_ops;
-        POp next = ops[0];
+        const POp* gops = p.ops + (size_t)cat * p.n_ops;
         for (int o = 0; o < p.n_ops; ++o) {
-            const POp op = next;
-            if (o + 1 < p.n_ops) next = ops[o + 1];          // prefetch: the load overlaps this op's work
+            POp op;
+            if (p.ops_in_smem) op = my_ops[o];
+            else op = gops[o];
             switch (op.type) {
             case OP_LEAF_SET2: {
                 // ---- a cherry in one pass: V = column(leaf 1) * column(leaf 2) ----
                 const double* mt1 = p.mt + (size_t)op.mat * p.mt_stride;
                 const double* mt2 = p.mt + (size_t)op.mat2 * p.mt_stride;
                 double* dst = slots + (size_t)op.a * L::SLOT_DOUBLES;
-                double v1[FT / CONSUMER_WARPS][MB], v2[FT / CONSUMER_WARPS][MB];
+                double v1[FPW][MB], v2[FPW][MB];
                 #pragma unroll
-                for (int fi = 0; fi < FT / CONSUMER_WARPS; ++fi) {
-                    const int f = warp * (FT / CONSUMER_WARPS) + fi;
+                for (int fi = 0; fi < FPW; ++fi) {
+                    const int f = wg * FPW + fi;
                     int o1, o2;
-                    if (p.counts_in_smem) { o1 = cnt_s[f * p.n_leaves + op.col]; o2 = cnt_s[f * p.n_leaves + op.col2]; }
+                    if (p.counts_in_smem) { o1 = my_cnt[f * p.n_leaves + op.col]; o2 = my_cnt[f * p.n_leaves + op.col2]; }
                     else {
                         int64_t fam = fam0 + f;
                         if (fam >= p.n_families) fam = p.n_families - 1;
@@ -156,14 +192,14 @@ __global__ void __launch_bounds__(PRUNE_THREADS, 1) prune_kernel(const PrunePara
                     }
                 }
                 #pragma unroll
-                for (int fi = 0; fi < FT / CONSUMER_WARPS; ++fi) {
-                    const int f = warp * (FT / CONSUMER_WARPS) + fi;
+                for (int fi = 0; fi < FPW; ++fi) {
+                    const int f = fbase + wg * FPW + fi;
                     double* row = dst + (size_t)f * LDV;
                     #pragma unroll
                     for (int i = 0; i < MB; ++i) row[lane + 32 * i] = v1[fi][i] * v2[fi][i];
                     if (lane == 0) slot_exp[op.a * FT + f] = 0;
                 }
-                consumer_sync();
+                group_sync(group);
                 break;
             }
             case OP_LEAF_SET:
@@ -173,12 +209,12 @@ __global__ void __launch_bounds__(PRUNE_THREADS, 1) prune_kernel(const PrunePara
                 const int col = op.col;
                 double* dst = slots + (size_t)op.a * L::SLOT_DOUBLES;
                 #pragma unroll
-                for (int fi = 0; fi < FT / CONSUMER_WARPS; ++fi) {
-                    const int f = warp * (FT / CONSUMER_WARPS) + fi;
+                for (int fi = 0; fi < FPW; ++fi) {
+                    const int fl = wg * FPW + fi;
                     int obs;
-                    if (p.counts_in_smem) obs = cnt_s[f * p.n_leaves + col];
+                    if (p.counts_in_smem) obs = my_cnt[fl * p.n_leaves + col];
                     else {
-                        int64_t fam = fam0 + f;
+                        int64_t fam = fam0 + fl;
                         if (fam >= p.n_families) fam = p.n_families - 1;
                         obs = p.counts[fam * p.n_leaves + col];
                     }
@@ -203,6 +239,7 @@ __global__ void __launch_bounds__(PRUNE_THREADS, 1) prune_kernel(const PrunePara
                             for (int i = 0; i < MB; ++i) v[i] = __dadd_rn(v[i], __dmul_rn(__ldg(src + lane + 32 * i), pe));
                         }
                     }
+                    const int f = fbase + fl;
                     double* row = dst + (size_t)f * LDV;
                     if (op.type == OP_LEAF_SET) {
                         #pragma unroll
@@ -214,7 +251,7 @@ __global__ void __launch_bounds__(PRUNE_THREADS, 1) prune_kernel(const PrunePara
                         for (int i = 0; i < MB; ++i) row[lane + 32 * i] *= v[i];
                     }
                 }
-                consumer_sync();
+                group_sync(group);
                 break;
             }
             case OP_GEMM_SET:
@@ -225,7 +262,7 @@ __global__ void __launch_bounds__(PRUNE_THREADS, 1) prune_kernel(const PrunePara
                 const bool is_set = (op.type == OP_GEMM_SET || op.type == OP_GEMM_SET_LEAF);
                 const bool with_leaf = (op.type == OP_GEMM_SET_LEAF || op.type == OP_GEMM_MUL_LEAF);
                 const int src_slot = is_set ? op.a : op.b;
-                const double* vsrc = slots + (size_t)src_slot * L::SLOT_DOUBLES + (size_t)(warp_n * 16 + g) * LDV + t4;
+                const double* vsrc = slots + (size_t)src_slot * L::SLOT_DOUBLES + (size_t)(fbase + g) * LDV + t4;
                 double acc[MB][2][2];
                 double lf[MB][2][2];       // leaf-sibling factor of each output element (1.0 when there is none)
                 #pragma unroll
@@ -235,16 +272,16 @@ __global__ void __launch_bounds__(PRUNE_THREADS, 1) prune_kernel(const PrunePara
                 }
                 if (with_leaf) {
                     // issued before the K loop so the L2 latency of the gather hides behind the MMAs
-                    const double* mt2 = p.mt + (size_t)op.mat2 * p.mt_stride + warp_m * 8 * MB + g;
+                    const double* mt2 = p.mt + (size_t)op.mat2 * p.mt_stride + wg * 8 * MB + g;
                     #pragma unroll
                     for (int nb = 0; nb < 2; ++nb)
                         #pragma unroll
                         for (int e = 0; e < 2; ++e) {
-                            const int f = warp_n * 16 + nb * 8 + t4 * 2 + e;
+                            const int fl = nb * 8 + t4 * 2 + e;
                             int obs;
-                            if (p.counts_in_smem) obs = cnt_s[f * p.n_leaves + op.col2];
+                            if (p.counts_in_smem) obs = my_cnt[fl * p.n_leaves + op.col2];
                             else {
-                                int64_t fam = fam0 + f;
+                                int64_t fam = fam0 + fl;
                                 if (fam >= p.n_families) fam = p.n_families - 1;
                                 obs = p.counts[fam * p.n_leaves + op.col2];
                             }
@@ -252,36 +289,72 @@ __global__ void __launch_bounds__(PRUNE_THREADS, 1) prune_kernel(const PrunePara
                             for (int i = 0; i < MB; ++i) lf[i][nb][e] = __ldg(mt2 + (size_t)obs * NR + i * 8);
                         }
                 }
-                const int a_off = (warp_m * 8 * MB) * 4 + lane;
-                for (int ch = 0; ch < p.n_kchunks; ++ch, ++pos) {
-                    const uint32_t stage = pos & stage_mask;
-                    mbar_wait(&full_bar[stage], (pos >> p.stage_shift) & 1);
+                if (lag_pending && group == 1) {
+                    // one-time stagger: start only after group 0 is lag_chunks stages into its first GEMM
+                    mbar_wait(lag_bar, 0);
+                    lag_pending = false;
+                }
+                // Fragments are double-buffered in registers: the loads of panel q+1 (possibly from the next
+                // ring stage) are issued before the MMAs of panel q, so shared-memory latency never gates the pipe.
+                const int a_off = (wg * 8 * MB) * 4 + lane;
+                double a0[MB], a1[MB], b00, b01, b10, b11;
+                uint32_t stage = pos & stage_mask;
+                mbar_wait(&full_bar[stage], (pos >> p.stage_shift) & 1);
+                {
                     const double* a_stage = ring + (size_t)stage * L::STAGE_DOUBLES + a_off;
                     #pragma unroll
-                    for (int pp = 0; pp < PPS; ++pp) {
-                        const int kcol = (ch * PPS + pp) * 4;
-                        double a[MB];
-                        #pragma unroll
-                        for (int i = 0; i < MB; ++i) a[i] = a_stage[pp * NR * 4 + i * 32];
-                        const double b0 = vsrc[kcol];
-                        const double b1 = vsrc[8 * LDV + kcol];
-                        #pragma unroll
-                        for (int i = 0; i < MB; ++i) {
-                            dmma_m8n8k4(acc[i][0][0], acc[i][0][1], a[i], b0);
-                            dmma_m8n8k4(acc[i][1][0], acc[i][1][1], a[i], b1);
-                        }
-                    }
-                    __syncwarp();
-                    if (lane == 0) mbar_arrive(&empty_bar[stage]);
+                    for (int i = 0; i < MB; ++i) a0[i] = a_stage[i * 32];
+                    b00 = vsrc[0];
+                    b01 = vsrc[8 * LDV];
                 }
-                if (is_set) consumer_sync();      // in place: every warp is done reading V_child before anyone overwrites it
+                #pragma unroll 1
+                for (int ch = 0; ch < p.n_kchunks; ++ch) {
+                    const double* a_stage = ring + (size_t)stage * L::STAGE_DOUBLES + a_off;
+                    const int kcol = ch * (PPS * 4);
+                    // panel 1 of this stage
+                    #pragma unroll
+                    for (int i = 0; i < MB; ++i) a1[i] = a_stage[NR * 4 + i * 32];
+                    b10 = vsrc[kcol + 4];
+                    b11 = vsrc[8 * LDV + kcol + 4];
+                    #pragma unroll
+                    for (int i = 0; i < MB; ++i) {
+                        dmma_m8n8k4(acc[i][0][0], acc[i][0][1], a0[i], b00);
+                        dmma_m8n8k4(acc[i][1][0], acc[i][1][1], a0[i], b01);
+                    }
+                    // panel 0 of the next stage
+                    const uint32_t npos = pos + 1;
+                    const uint32_t nstage = npos & stage_mask;
+                    if (ch + 1 < p.n_kchunks) {
+                        mbar_wait(&full_bar[nstage], (npos >> p.stage_shift) & 1);
+                        const double* n_stage = ring + (size_t)nstage * L::STAGE_DOUBLES + a_off;
+                        #pragma unroll
+                        for (int i = 0; i < MB; ++i) a0[i] = n_stage[i * 32];
+                        b00 = vsrc[kcol + 8];
+                        b01 = vsrc[8 * LDV + kcol + 8];
+                    }
+                    #pragma unroll
+                    for (int i = 0; i < MB; ++i) {
+                        dmma_m8n8k4(acc[i][0][0], acc[i][0][1], a1[i], b10);
+                        dmma_m8n8k4(acc[i][1][0], acc[i][1][1], a1[i], b11);
+                    }
+                    // every load of this stage has been consumed by an MMA above
+                    __syncwarp();
+                    if (lane == 0) {
+                        mbar_arrive(&empty_bar[stage]);
+                        if (lag_pending && ch == p.lag_chunks - 1) mbar_arrive(lag_bar);
+                    }
+                    if (ch == p.lag_chunks - 1) lag_pending = false;
+                    stage = nstage;
+                    pos = npos;
+                }
+                if (is_set) group_sync(group);      // in place: every warp of the group is done reading V_child before anyone overwrites it
                 double* dst = slots + (size_t)op.a * L::SLOT_DOUBLES;
                 #pragma unroll
                 for (int i = 0; i < MB; ++i) {
-                    const int s = warp_m * 8 * MB + i * 8 + g;
+                    const int s = wg * 8 * MB + i * 8 + g;
                     #pragma unroll
                     for (int nb = 0; nb < 2; ++nb) {
-                        const int f = warp_n * 16 + nb * 8 + t4 * 2;
+                        const int f = fbase + nb * 8 + t4 * 2;
                         double* q0 = dst + (size_t)f * LDV + s;
                         double* q1 = q0 + LDV;
                         const double y0 = acc[i][nb][0] * lf[i][nb][0];
@@ -290,24 +363,25 @@ __global__ void __launch_bounds__(PRUNE_THREADS, 1) prune_kernel(const PrunePara
                         else { *q0 *= y0; *q1 *= y1; }
                     }
                 }
-                if (!is_set && p.rescale && tid < FT) slot_exp[op.a * FT + tid] += slot_exp[op.b * FT + tid];
-                consumer_sync();
+                if (!is_set && p.rescale && gtid < GFT) slot_exp[op.a * FT + fbase + gtid] += slot_exp[op.b * FT + fbase + gtid];
+                group_sync(group);
                 break;
             }
             case OP_SPILL:
             case OP_FILL: {
-                double* sl = slots + (size_t)op.a * L::SLOT_DOUBLES;
-                double* sc = p.scratch + ((size_t)blockIdx.x * p.n_spill + op.b) * L::SLOT_DOUBLES;
-                int* sce = p.scratch_exp + ((size_t)blockIdx.x * p.n_spill + op.b) * FT;
+                // this group's half of the slot (families fbase .. fbase+GFT-1 are contiguous rows)
+                double* sl = slots + (size_t)op.a * L::SLOT_DOUBLES + (size_t)fbase * LDV;
+                double* sc = p.scratch + ((size_t)blockIdx.x * p.n_spill + op.b) * L::SLOT_DOUBLES + (size_t)fbase * LDV;
+                int* sce = p.scratch_exp + ((size_t)blockIdx.x * p.n_spill + op.b) * FT + fbase;
                 if (op.type == OP_SPILL) {
-                    for (int i = tid; i < L::SLOT_DOUBLES; i += CONSUMER_THREADS) sc[i] = sl[i];
-                    if (tid < FT) sce[tid] = slot_exp[op.a * FT + tid];
+                    for (int i = gtid; i < GFT * LDV; i += GROUP_THREADS) sc[i] = sl[i];
+                    if (gtid < GFT) sce[gtid] = slot_exp[op.a * FT + fbase + gtid];
                 }
                 else {
-                    for (int i = tid; i < L::SLOT_DOUBLES; i += CONSUMER_THREADS) sl[i] = sc[i];
-                    if (tid < FT) slot_exp[op.a * FT + tid] = sce[tid];
+                    for (int i = gtid; i < GFT * LDV; i += GROUP_THREADS) sl[i] = sc[i];
+                    if (gtid < GFT) slot_exp[op.a * FT + fbase + gtid] = sce[gtid];
                 }
-                consumer_sync();
+                group_sync(group);
                 break;
             }
             case OP_RESCALE: {
@@ -315,8 +389,8 @@ __global__ void __launch_bounds__(PRUNE_THREADS, 1) prune_kernel(const PrunePara
                 if (!p.rescale) break;          // uniform: reference arithmetic, no renormalisation
                 double* sl = slots + (size_t)op.a * L::SLOT_DOUBLES;
                 #pragma unroll
-                for (int fi = 0; fi < FT / CONSUMER_WARPS; ++fi) {
-                    const int f = warp * (FT / CONSUMER_WARPS) + fi;
+                for (int fi = 0; fi < FPW; ++fi) {
+                    const int f = fbase + wg * FPW + fi;
                     double* row = sl + (size_t)f * LDV;
                     double m = 0.0;
                     for (int s = lane; s <= p.mf; s += 32) m = fmax(m, row[s]);
@@ -330,16 +404,17 @@ __global__ void __launch_bounds__(PRUNE_THREADS, 1) prune_kernel(const PrunePara
                         if (lane == 0) slot_exp[op.a * FT + f] += e;
                     }
                 }
-                consumer_sync();
+                group_sync(group);
                 break;
             }
             case OP_ROOT: {
                 // ---- root: index j <-> root size j+1 (src/base_model.cpp:95-98) ----
                 const double* sl = slots + (size_t)op.a * L::SLOT_DOUBLES;
                 #pragma unroll
-                for (int fi = 0; fi < FT / CONSUMER_WARPS; ++fi) {
-                    const int f = warp * (FT / CONSUMER_WARPS) + fi;
-                    const int64_t fam = fam0 + f;
+                for (int fi = 0; fi < FPW; ++fi) {
+                    const int fl = wg * FPW + fi;
+                    const int f = fbase + fl;
+                    const int64_t fam = fam0 + fl;
                     if (fam >= p.n_families) continue;      // warp-uniform
                     const double* row = sl + (size_t)f * LDV;
                     const int e = p.rescale ? slot_exp[op.a * FT + f] : 0;
