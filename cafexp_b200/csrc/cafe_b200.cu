@@ -462,9 +462,9 @@ int launch_prune_mb(cafe_b200_ctx* c, const PruneParams& p)
     q.ops_in_smem = (L::total_bytes(c->n_slots, c->n_stages, ops_bytes) <= c->smem_optin) ? 1 : 0;
     const int smem = L::total_bytes(c->n_slots, c->n_stages, q.ops_in_smem ? ops_bytes : 0);
     CUDA_TRY(c, cudaFuncSetAttribute(prune_kernel<MB>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
-    const int64_t items = q.n_tiles * q.n_categories;
-    const int grid = (int)std::min<int64_t>(items, c->sm_count);
-    prune_kernel<MB><<<grid, PRUNE_THREADS, smem, c->stream>>>(q);
+    const int64_t items = q.n_tiles * q.n_categories;        // one item = one group's 16-family tile of one category
+    const int grid = (int)std::min<int64_t>((items + GROUPS - 1) / GROUPS, c->sm_count);
+    prune_kernel<MB><<<grid, PRUNE2_THREADS, smem, c->stream>>>(q);
     CUDA_TRY(c, cudaGetLastError());
     c->launches++;
     return CAFE_B200_OK;
@@ -479,11 +479,9 @@ int launch_prune(cafe_b200_ctx* c, int k, int mode, double* root_out)
     p.mf = c->mf; p.mrf = c->mrf; p.n_ops = c->n_pops; p.n_kchunks = c->n_kchunks; p.mode = mode;
     p.rescale = c->rescale; p.n_spill = std::max(1, c->sched.n_spill); p.err_rows = c->err_rows; p.err_ndev = c->err_ndev;
     p.counts_in_smem = (FT * c->n_leaves * 2 <= CNT_CAP_BYTES) ? 1 : 0;
-    p.n_slots = c->n_slots; p.n_tiles = c->n_tiles;
-    p.n_stages = c->n_stages; p.stage_shift = c->n_stages == 8 ? 3 : (c->n_stages == 4 ? 2 : 1);
-    // group 1 trails group 0 by half the ring (the other half stays available for the producer's prefetch)
-    p.lag_chunks = std::min(c->n_stages / 2, c->n_kchunks - 1);
-    if (const char* e = getenv("CAFE_B200_LAG")) p.lag_chunks = std::max(0, std::min(atoi(e), std::min(c->n_stages, c->n_kchunks) - 1));
+    p.n_slots = c->n_slots; p.n_tiles = (c->n_families + GFT - 1) / GFT;
+    // the ring is split between the two consumer groups: c->n_stages in {8,4,2} -> {4,2,1} stages each
+    p.n_stages = c->n_stages / GROUPS; p.stage_shift = p.n_stages == 4 ? 2 : (p.n_stages == 2 ? 1 : 0);
     p.ops = c->d_pops; p.counts = c->d_counts;
     p.mp = c->d_mp; p.mt = c->d_mt; p.mp_stride = c->mp_stride; p.mt_stride = c->mt_stride;
     p.err = c->d_err; p.prior = c->d_prior; p.logprior = c->d_logprior; p.cat_probs = c->d_catprobs;

@@ -80,11 +80,10 @@ struct PruneParams {
     int err_ndev;
     int counts_in_smem;
     int n_slots;
-    int n_stages;           // ring depth (power of two)
+    int n_stages;           // ring depth of one consumer group (power of two)
     int stage_shift;        // log2(n_stages)
     int ops_in_smem;        // per-group copies of the op list live in shared memory
-    int lag_chunks;         // ring stages by which consumer group 1 trails group 0 (0 = no stagger)
-    int64_t n_tiles;
+    int64_t n_tiles;        // tiles of FT/2 families (one per consumer group and work item)
     // device pointers
     const POp* ops;                 // [k][n_ops]
     const int32_t* counts;          // [F][n_leaves]

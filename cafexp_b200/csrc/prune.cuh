@@ -18,14 +18,17 @@
 // streams from L2 through a shared-memory ring filled by 1-D bulk async copies (TMA engine,
 // cp.async.bulk + mbarrier complete_tx) issued by a dedicated producer warp that runs ahead across ops.
 //
-// The 8 consumer warps form TWO INDEPENDENT GROUPS of 4 warps; group g owns families [16g, 16g+16) of
-// the tile (its half of every slot), has its own named barrier, and walks the same op list, so both
-// groups consume the SAME matrix stream from the shared ring (a stage is released when all 8 warps
-// have read it) — L2 traffic per flop is that of a 32-family tile.  Group 1 starts LAG chunks behind
-// group 0 and the offset persists, so while one group is between GEMMs (epilogue, child product, leaf
-// gathers, barriers) the other keeps the FP64 tensor pipe busy; each SM sub-partition hosts one warp of
-// each group.  Inside a GEMM the A/B fragments are double-buffered in registers across ring stages, so
-// a warp running alone can still issue DMMAs back to back.
+// The 8 consumer warps form TWO INDEPENDENT GROUPS of 4 warps (one warp per SM sub-partition each).  A group
+// is a virtual thread block: it owns families [16g, 16g+16) of every slot, its own half of the matrix ring,
+// its own named barrier and its own stream of work items (16-family tiles), so nothing couples the two groups
+// except the FP64 tensor pipe they share.  While one group is between GEMMs (epilogue, child product, leaf
+// gathers, barriers, waiting for L2) the other has the pipe to itself and consumes chunks twice as fast.
+// Each group's ring is fed by PRODUCERS_PER_GROUP producer warps taking alternate chunks: one elected thread
+// needs ~300-400 cycles per chunk (try_wait on the empty barrier ~90, expect_tx, bulk-copy issue, address
+// arithmetic — measured), which is as long as a lone group needs to consume it, so a single producer per group
+// would pin the group to the shared-pipe rate and the decoupling would buy nothing (measured: 0.65 of peak
+// either way).  Inside a GEMM the A/B fragments are double-buffered in registers across ring stages, so a warp
+// running alone can still issue DMMAs back to back.
 //
 // The epilogue multiplies the product straight into the parent's accumulator slot (child product);
 // leaf edges are gathers of one matrix column (or an error-model stencil of columns), not GEMMs.
@@ -41,6 +44,8 @@ constexpr int GROUP_WARPS = CONSUMER_WARPS / GROUPS;     // 4: one per SM sub-pa
 constexpr int GROUP_THREADS = GROUP_WARPS * 32;
 constexpr int GFT = FT / GROUPS;                         // 16 families per group = 2 n8 blocks
 constexpr int FPW = GFT / GROUP_WARPS;                   // 4 families per warp in the gather / root ops
+constexpr int PRODUCERS_PER_GROUP = 2;                   // producer warps per group, taking alternate chunks
+constexpr int PRUNE2_THREADS = CONSUMER_THREADS + GROUPS * PRODUCERS_PER_GROUP * 32;
 
 template <int MB>
 struct PruneSmem {
@@ -69,44 +74,49 @@ __device__ __forceinline__ void group_sync(int group)
 }
 
 template <int MB>
-__global__ void __launch_bounds__(PRUNE_THREADS, 1) prune_kernel(const PruneParams p)
+__global__ void __launch_bounds__(PRUNE2_THREADS, 1) prune_kernel(const PruneParams p)
 {
     using L = PruneSmem<MB>;
     constexpr int NR = L::NR;
     constexpr int LDV = L::LDV;
     extern __shared__ __align__(128) unsigned char smem_raw[];
     double* ring = reinterpret_cast<double*>(smem_raw);
-    const int ring_bytes = L::ring_bytes(p.n_stages);
+    const int ring_bytes = L::ring_bytes(GROUPS * p.n_stages);      // p.n_stages = ring depth of ONE group
     const uint32_t stage_mask = (uint32_t)p.n_stages - 1u;
     double* slots = reinterpret_cast<double*>(smem_raw + ring_bytes);
     uint16_t* cnt_s = reinterpret_cast<uint16_t*>(smem_raw + ring_bytes + p.n_slots * L::SLOT_BYTES);
     uint64_t* full_bar = reinterpret_cast<uint64_t*>(smem_raw + ring_bytes + p.n_slots * L::SLOT_BYTES + CNT_CAP_BYTES);
     uint64_t* empty_bar = full_bar + MAX_STAGES;
-    uint64_t* lag_bar = empty_bar + MAX_STAGES;
     int* slot_exp = reinterpret_cast<int*>(smem_raw + ring_bytes + p.n_slots * L::SLOT_BYTES + CNT_CAP_BYTES + L::MISC_BYTES);
-    POp* ops_s = reinterpret_cast<POp*>(smem_raw + L::fixed_bytes(p.n_slots, p.n_stages));
+    POp* ops_s = reinterpret_cast<POp*>(smem_raw + L::fixed_bytes(p.n_slots, GROUPS * p.n_stages));
 
     const int tid = threadIdx.x;
     const int warp = tid >> 5;
     const int lane = tid & 31;
 
     if (tid == 0) {
-        for (int s = 0; s < p.n_stages; ++s) {
+        for (int s = 0; s < GROUPS * p.n_stages; ++s) {
             mbar_init(&full_bar[s], 1);
-            mbar_init(&empty_bar[s], CONSUMER_WARPS);
+            mbar_init(&empty_bar[s], GROUP_WARPS);
         }
-        mbar_init(lag_bar, GROUP_WARPS);
         fence_barrier_init();
     }
     __syncthreads();
 
     const int64_t n_items = p.n_tiles * p.n_categories;
 
-    if (warp == CONSUMER_WARPS) {
-        // ===================== producer: stream matrix K-chunks into the ring =====================
+    const int64_t vstride = (int64_t)gridDim.x * GROUPS;
+
+    if (warp >= CONSUMER_WARPS) {
+        // ===== producers: warp (group, lane_of_group) streams chunks pos = lane_of_group (mod PRODUCERS_PER_GROUP) =====
+        const int group = (warp - CONSUMER_WARPS) / PRODUCERS_PER_GROUP;
+        const int which = (warp - CONSUMER_WARPS) % PRODUCERS_PER_GROUP;
         if (lane == 0) {
+            double* gring = ring + (size_t)group * p.n_stages * L::STAGE_DOUBLES;
+            uint64_t* gfull = full_bar + group * p.n_stages;
+            uint64_t* gempty = empty_bar + group * p.n_stages;
             uint32_t pos = 0;
-            for (int64_t item = blockIdx.x; item < n_items; item += gridDim.x) {
+            for (int64_t item = (int64_t)blockIdx.x * GROUPS + group; item < n_items; item += vstride) {
                 const int cat = (int)(item / p.n_tiles);
                 const POp* ops = p.ops + (size_t)cat * p.n_ops;
                 for (int o = 0; o < p.n_ops; ++o) {
@@ -114,11 +124,12 @@ __global__ void __launch_bounds__(PRUNE_THREADS, 1) prune_kernel(const PrunePara
                     if (type != OP_GEMM_SET && type != OP_GEMM_MUL && type != OP_GEMM_SET_LEAF && type != OP_GEMM_MUL_LEAF) continue;
                     const double* src = p.mp + (size_t)ops[o].mat * p.mp_stride;
                     for (int ch = 0; ch < p.n_kchunks; ++ch, ++pos) {
+                        if ((int)(pos % PRODUCERS_PER_GROUP) != which) continue;
                         const uint32_t stage = pos & stage_mask;
                         const uint32_t round = pos >> p.stage_shift;
-                        mbar_wait(&empty_bar[stage], (round & 1) ^ 1);
-                        mbar_arrive_expect_tx(&full_bar[stage], L::STAGE_BYTES);
-                        bulk_copy_g2s(ring + (size_t)stage * L::STAGE_DOUBLES, src + (size_t)ch * L::STAGE_DOUBLES, L::STAGE_BYTES, &full_bar[stage]);
+                        mbar_wait(&gempty[stage], (round & 1) ^ 1);
+                        mbar_arrive_expect_tx(&gfull[stage], L::STAGE_BYTES);
+                        bulk_copy_g2s(gring + (size_t)stage * L::STAGE_DOUBLES, src + (size_t)ch * L::STAGE_DOUBLES, L::STAGE_BYTES, &gfull[stage]);
                     }
                 }
             }
@@ -134,15 +145,17 @@ __global__ void __launch_bounds__(PRUNE_THREADS, 1) prune_kernel(const PrunePara
     const int t4 = lane & 3;
     const int fbase = group * GFT;                // first tile family of this group
     uint32_t pos = 0;
-    bool lag_pending = (p.lag_chunks > 0);        // group 0 signals once, group 1 waits once
     int ops_cat = -1;
+    ring += (size_t)group * p.n_stages * L::STAGE_DOUBLES;      // this group's half of the ring
+    full_bar += group * p.n_stages;
+    empty_bar += group * p.n_stages;
     POp* my_ops = ops_s + (size_t)group * p.n_ops;
     uint16_t* my_cnt = cnt_s + (size_t)fbase * p.n_leaves;
 
-    for (int64_t item = blockIdx.x; item < n_items; item += gridDim.x) {
+    for (int64_t item = (int64_t)blockIdx.x * GROUPS + group; item < n_items; item += vstride) {
         const int cat = (int)(item / p.n_tiles);
         const int64_t tile = item % p.n_tiles;
-        const int64_t fam0 = tile * FT + fbase;   // first family of this group
+        const int64_t fam0 = tile * GFT;          // first family of this group's tile
 
         group_sync(group);      // previous item fully finished with this group's shared memory
         if (p.counts_in_smem) {
@@ -289,11 +302,6 @@ __global__ void __launch_bounds__(PRUNE_THREADS, 1) prune_kernel(const PrunePara
                             for (int i = 0; i < MB; ++i) lf[i][nb][e] = __ldg(mt2 + (size_t)obs * NR + i * 8);
                         }
                 }
-                if (lag_pending && group == 1) {
-                    // one-time stagger: start only after group 0 is lag_chunks stages into its first GEMM
-                    mbar_wait(lag_bar, 0);
-                    lag_pending = false;
-                }
                 // Fragments are double-buffered in registers: the loads of panel q+1 (possibly from the next
                 // ring stage) are issued before the MMAs of panel q, so shared-memory latency never gates the pipe.
                 const int a_off = (wg * 8 * MB) * 4 + lane;
@@ -339,11 +347,7 @@ __global__ void __launch_bounds__(PRUNE_THREADS, 1) prune_kernel(const PrunePara
                     }
                     // every load of this stage has been consumed by an MMA above
                     __syncwarp();
-                    if (lane == 0) {
-                        mbar_arrive(&empty_bar[stage]);
-                        if (lag_pending && ch == p.lag_chunks - 1) mbar_arrive(lag_bar);
-                    }
-                    if (ch == p.lag_chunks - 1) lag_pending = false;
+                    if (lane == 0) mbar_arrive(&empty_bar[stage]);
                     stage = nstage;
                     pos = npos;
                 }
