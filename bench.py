@@ -207,6 +207,16 @@ def measure_fp64_peak():
     return dmma, d.get("cublas_dgemm_8192_sustained_tflops"), src
 
 
+def measured_traffic(families_per_launch):
+    """DRAM bytes per launch of the pruning kernel from the committed ncu capture (profiles/prune_traffic.json),
+    scaled per family; None when no capture is committed."""
+    try:
+        d = json.load(open(os.path.join(ROOT, "profiles", "prune_traffic.json")))
+        return float(d["bytes_per_family"]) * families_per_launch, d["source"]
+    except Exception:
+        return None, None
+
+
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
@@ -333,6 +343,7 @@ def main():
         fam_local = last - first
         prune_s = float(prune_avg.item()) / 1e3
         achieved = flops_fc * K * fam_local / prune_s / 1e12 if prune_s > 0 else 0.0
+        traffic, traffic_src = measured_traffic(fam_local)
         line = {
             "metric": "family-likelihood evals/sec", "value": F * args.steps / (total_ms / 1e3), "unit": "families/s", "n_gpus": world,
             "steps": args.steps, "warmup": max(args.warmup, 1), "ms_per_step": total_ms / args.steps, "higher_is_better": True,
@@ -340,7 +351,8 @@ def main():
             "family_category_evals_per_s": F * K * args.steps / (total_ms / 1e3),
             "neg_lnl": neg_lnl, "clocks": clocks, "gpu_launches": int(launches), "e2e": e2e,
             "roofline": {"bound": "tensor", "kernel": "cafe::prune_kernel<5> (FP64 DMMA pruning)", "achieved": achieved, "peak": peak_dmma,
-                         "unit": "TFLOP/s", "frac": achieved / peak_dmma if peak_dmma else None, "traffic": None,
+                         "unit": "TFLOP/s", "frac": achieved / peak_dmma if peak_dmma else None, "traffic": traffic, "traffic_unit": "bytes/launch",
+                         "traffic_source": traffic_src, "algorithmic_bytes": (N_LEAVES * 4 + 8 * (K + 1)) * fam_local,
                          "peak_source": f"FP64 mma.sync peak, {peak_src}; cuBLAS DGEMM 8192^3 sustained = {peak_cublas} TFLOP/s; MEASURED_PEAKS.json has no FP64 entry",
                          "flops_per_family_category": flops_fc, "families_per_launch": fam_local, "categories": K,
                          "kernel_ms": prune_s * 1e3, "matrix_build_ms": float(np.mean(build_ms)),
