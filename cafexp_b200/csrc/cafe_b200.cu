@@ -20,6 +20,7 @@
 #include "common.cuh"
 #include "prune.cuh"
 #include "pupko.cuh"
+#include "pvalue.cuh"
 #include "reduce.cuh"
 
 using namespace cafe;
@@ -930,6 +931,59 @@ int cafe_b200_prune_roots(cafe_b200_ctx* c, const double* lambdas, int n_lambdas
     }
     cudaFree(d_root);
     return rc;
+}
+
+int cafe_b200_root_max(cafe_b200_ctx* c, const double* lambdas, int n_lambdas, double* out)
+{
+    if (!c || !lambdas || !out) return fail(c, CAFE_B200_ERR_ARG, "bad argument to root_max");
+    CUDA_TRY(c, cudaSetDevice(c->device));
+    int rc = check_counts(c);
+    if (rc) return rc;
+    std::vector<double> ones(c->n, 1.0);
+    const double cp = 1.0;
+    rc = stage_and_build(c, lambdas, n_lambdas, 1, &cp, ones.data(), c->n);
+    if (rc) return rc;
+    rc = launch_prune(c, 1, CAFE_B200_ROOT_MAX, nullptr);
+    if (rc) return rc;
+    CUDA_TRY(c, cudaEventRecord(c->ev[2], c->stream));
+    c->ev_valid[2] = true; c->ev_valid[3] = c->ev_valid[4] = false;
+    CUDA_TRY(c, cudaMemcpyAsync(out, c->d_cat_lk, (size_t)c->n_families * sizeof(double), cudaMemcpyDeviceToHost, c->stream));
+    CUDA_TRY(c, cudaStreamSynchronize(c->stream));
+    c->evals++;
+    return CAFE_B200_OK;
+}
+
+int cafe_b200_pvalues(int device, const double* cond, int n_root_sizes, int n_sim, const double* observed, int64_t n_families, double* pvalues)
+{
+    if (!cond || !observed || !pvalues || n_root_sizes < 1 || n_sim < 1 || n_families < 0) return fail(nullptr, CAFE_B200_ERR_ARG, "bad argument to pvalues");
+    if (n_sim > PV_MAX_SIM) return fail(nullptr, CAFE_B200_ERR_LIMIT, "more simulations per root size than one thread block sorts (4096)");
+    int ndev = 0;
+    if (cudaGetDeviceCount(&ndev) != cudaSuccess || ndev == 0) {
+        cudaGetLastError();
+        return fail(nullptr, CAFE_B200_ERR_CUDA, "no CUDA device: this engine has no CPU fallback");
+    }
+    if (device < 0 || device >= ndev) return fail(nullptr, CAFE_B200_ERR_ARG, "device ordinal out of range");
+    if (n_families == 0) return CAFE_B200_OK;
+    double *d_cond = nullptr, *d_obs = nullptr, *d_p = nullptr;
+    const size_t nc = (size_t)n_root_sizes * n_sim;
+    cudaError_t e = cudaSetDevice(device);
+    if (e == cudaSuccess) e = dev_alloc(&d_cond, nc);
+    if (e == cudaSuccess) e = dev_alloc(&d_obs, (size_t)n_families);
+    if (e == cudaSuccess) e = dev_alloc(&d_p, (size_t)n_families);
+    if (e == cudaSuccess) e = cudaMemcpy(d_cond, cond, nc * sizeof(double), cudaMemcpyHostToDevice);
+    if (e == cudaSuccess) e = cudaMemcpy(d_obs, observed, (size_t)n_families * sizeof(double), cudaMemcpyHostToDevice);
+    if (e == cudaSuccess) {
+        int padded = 1;
+        while (padded < n_sim) padded <<= 1;
+        sort_rows_kernel<<<n_root_sizes, PV_THREADS, (size_t)padded * sizeof(double)>>>(d_cond, n_sim, padded);
+        const int blocks = (int)((n_families + PV_THREADS - 1) / PV_THREADS);
+        pvalue_kernel<<<blocks, PV_THREADS>>>(d_cond, n_root_sizes, n_sim, d_obs, n_families, d_p);
+        e = cudaGetLastError();
+    }
+    if (e == cudaSuccess) e = cudaMemcpy(pvalues, d_p, (size_t)n_families * sizeof(double), cudaMemcpyDeviceToHost);
+    cudaFree(d_cond); cudaFree(d_obs); cudaFree(d_p);
+    if (e != cudaSuccess) return fail(nullptr, CAFE_B200_ERR_CUDA, std::string("pvalues: ") + cudaGetErrorString(e));
+    return CAFE_B200_OK;
 }
 
 int cafe_b200_reconstruct(cafe_b200_ctx* c, const double* lambdas, int n_lambdas, int k, const double* prior_by_size, int32_t* states)

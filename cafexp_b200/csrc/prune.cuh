@@ -426,7 +426,20 @@ __global__ void __launch_bounds__(PRUNE2_THREADS, 1) prune_kernel(const PrunePar
                         double* out = p.root_out + ((size_t)fam * p.n_categories + cat) * p.mrf;
                         for (int j = lane; j < p.mrf; j += 32) out[j] = e ? ldexp(row[j + 1], e) : row[j + 1];
                     }
-                    if (p.mode == 0) {
+                    if (p.mode == 2) {
+                        // max_j L[j], no prior: the statistic of get_random_probabilities / compute_tree_pvalue
+                        // (src/probability.cpp:308, 399)
+                        double best = 0.0;
+                        for (int j = lane; j < p.mrf; j += 32) {
+                            double lj = row[j + 1];
+                            if (e) lj = ldexp(lj, e);
+                            best = fmax(best, lj);
+                        }
+                        #pragma unroll
+                        for (int off = 16; off > 0; off >>= 1) best = fmax(best, __shfl_xor_sync(0xffffffffu, best, off));
+                        if (lane == 0) { p.cat_lk[fam] = best; p.fail[fam] = 0; }
+                    }
+                    else if (p.mode == 0) {
                         // max_j( log L[j] + log prior[j] )
                         double best = -INFINITY;
                         for (int j = lane; j < p.mrf; j += 32) {

@@ -27,7 +27,7 @@ EXPORTS = [
     "cafe_b200_abi_version", "cafe_b200_get_limits", "cafe_b200_device_count", "cafe_b200_create", "cafe_b200_destroy",
     "cafe_b200_last_error", "cafe_b200_set_families", "cafe_b200_set_error_model", "cafe_b200_set_option", "cafe_b200_set_stream",
     "cafe_b200_eval", "cafe_b200_eval_device", "cafe_b200_reconstruct", "cafe_b200_build_matrices", "cafe_b200_matrix_size",
-    "cafe_b200_prune_roots", "cafe_b200_launch_count", "cafe_b200_last_timings",
+    "cafe_b200_prune_roots", "cafe_b200_launch_count", "cafe_b200_last_timings", "cafe_b200_root_max", "cafe_b200_pvalues",
 ]
 
 _dp = C.POINTER(C.c_double)
@@ -89,6 +89,10 @@ def load_library():
     L.cafe_b200_matrix_size.argtypes = [C.c_void_p]
     L.cafe_b200_prune_roots.restype = C.c_int
     L.cafe_b200_prune_roots.argtypes = [C.c_void_p, _dp, C.c_int, C.c_int, _dp]
+    L.cafe_b200_root_max.restype = C.c_int
+    L.cafe_b200_root_max.argtypes = [C.c_void_p, _dp, C.c_int, _dp]
+    L.cafe_b200_pvalues.restype = C.c_int
+    L.cafe_b200_pvalues.argtypes = [C.c_int, _dp, C.c_int, C.c_int, _dp, C.c_int64, _dp]
     L.cafe_b200_launch_count.restype = C.c_int64
     L.cafe_b200_launch_count.argtypes = [C.c_void_p]
     L.cafe_b200_last_timings.restype = C.c_int
@@ -225,6 +229,14 @@ class Engine:
         return states
 
     # -- inspection -----------------------------------------------------------------------------
+    def root_max(self, lambdas):
+        """max_j of every family's root vector under one lambda set (cafe_b200_root_max): the likelihood
+        compute_pvalues uses for simulated and observed families alike (src/probability.cpp:308, 399)."""
+        lam = np.ascontiguousarray(lambdas, np.float64).ravel()
+        out = np.zeros(self.n_families)
+        self._check(self._lib.cafe_b200_root_max(self._h, _d(lam), lam.size, _d(out)), "cafe_b200_root_max")
+        return out
+
     def build_matrices(self, lambdas):
         lam, k, nl = self._lams(lambdas)
         out = np.empty((k, self.tree.n_nodes, self.matrix_size, self.mf + 1))
@@ -245,6 +257,20 @@ class Engine:
         ms = np.zeros(4)
         self._lib.cafe_b200_last_timings(self._h, _d(ms))
         return {"matrix_build": ms[0], "prune": ms[1], "reduce": ms[2], "reconstruct": ms[3]}
+
+
+def pvalues(cond, observed, device: int = 0) -> np.ndarray:
+    """p-value of every observed likelihood against the simulated conditional distributions
+    (cafe_b200_pvalues; pvalue / compute_tree_pvalue, src/probability.cpp:379-409).
+    cond: [n_root_sizes][n_sim] unsorted; observed: [F]."""
+    L = load_library()
+    cond = np.ascontiguousarray(cond, np.float64)
+    obs = np.ascontiguousarray(observed, np.float64)
+    out = np.zeros(len(obs))
+    rc = L.cafe_b200_pvalues(device, _d(cond), cond.shape[0], cond.shape[1], _d(obs), len(obs), _d(out))
+    if rc:
+        raise RuntimeError(f"cafe_b200_pvalues failed ({rc}): {L.cafe_b200_last_error(None).decode()}")
+    return out
 
 
 def neg_inf_safe(x: float) -> float:

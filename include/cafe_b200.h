@@ -42,8 +42,9 @@ enum {
 /* mode of cafe_b200_eval */
 enum {
     CAFE_B200_BASE_LOGMAX = 0,  /* base_model: lnL_i = max_j(log L_i[j] + log prior[j])         src/base_model.cpp:89-106 */
-    CAFE_B200_GAMMA_LINSUM = 1  /* gamma_model: lnL_i = log sum_k max_j(L_ik[j] prior[j]) catprob[k], fail if sum_j L_ik[j]==0
+    CAFE_B200_GAMMA_LINSUM = 1, /* gamma_model: lnL_i = log sum_k max_j(L_ik[j] prior[j]) catprob[k], fail if sum_j L_ik[j]==0
                                                                                                   src/gamma_core.cpp:144-166,203-219 */
+    CAFE_B200_ROOT_MAX = 2      /* internal to cafe_b200_root_max: lk_i = max_j L_i[j], no prior  src/probability.cpp:308,399 */
 };
 
 /* options for cafe_b200_set_option */
@@ -137,6 +138,27 @@ int  cafe_b200_eval_device(cafe_b200_ctx* ctx, const double* lambdas, int n_lamb
  *   states  out HOST [n_families][n_categories][n_internal] int32, internal nodes in tree order (root last) */
 int  cafe_b200_reconstruct(cafe_b200_ctx* ctx, const double* lambdas, int n_lambdas, int n_categories,
                            const double* prior_by_size, int32_t* states);
+
+/* ---- family p-values (compute_pvalues, src/probability.cpp:411-444) ------------------------- */
+
+/* The statistic both halves of compute_pvalues use: lk_i = max_j of the root partial-likelihood vector of family i
+ * under one lambda set (no rate categories, no prior) = *max_element(inference root vector), src/probability.cpp:308
+ * (simulated families, get_random_probabilities) and :399 (observed families, compute_tree_pvalue).
+ *   lambdas HOST [n_lambdas] RAW;  out HOST [n_families].
+ * The caller simulates the families on the host with the reference's own generator (std::mt19937 randomizer_engine +
+ * set_weighted_random_family_size, src/probability.cpp:320-351) so that the random stream stays the reference's, builds
+ * a context over them and calls this; the observed families go through their own context. */
+int  cafe_b200_root_max(cafe_b200_ctx* ctx, const double* lambdas, int n_lambdas, double* out);
+
+/* p-value of every observed family against the simulated conditional distributions:
+ *   cond      HOST [n_root_sizes][n_sim] likelihoods of the simulated families, row s = root size s, UNSORTED
+ *             (sorted on the device, src/probability.cpp:310)
+ *   observed  HOST [n_families] likelihoods of the observed families
+ *   pvalues   out HOST [n_families] = max_s idx_s / n_sim, idx_s = upper_bound(cond[s], observed_i) - begin, or
+ *             n_sim - 1 when no simulated value is greater (pvalue + compute_tree_pvalue, src/probability.cpp:379-409)
+ * Stateless; n_sim <= 4096. */
+int  cafe_b200_pvalues(int device, const double* cond, int n_root_sizes, int n_sim, const double* observed,
+                       int64_t n_families, double* pvalues);
 
 /* ---- inspection entry points used by the parity tests ------------------------------------- */
 

@@ -17,6 +17,7 @@
 #include "io.h"
 #include "lambda.h"
 #include "matrix_cache.h"
+#include "probability.h"
 #include "root_distribution.h"
 #include "root_equilibrium_distribution.h"
 #include "user_data.h"
@@ -185,6 +186,13 @@ long cuda_bridge::evaluate(const std::vector<double>& lambdas, const std::vector
           "cafe_b200_eval");
     for (int64_t i = 0; i < n_failed; ++i) failed[failed_idx[i]] = 1;
     return (long)n_failed;
+}
+
+std::vector<double> cuda_bridge::root_max(const std::vector<double>& lambdas)
+{
+    std::vector<double> out(_n_unique, 0.0);
+    check(cafe_b200_root_max(_ctx, lambdas.data(), (int)_order.size(), out.data()), "cafe_b200_root_max");
+    return out;
 }
 
 void cuda_bridge::reconstruct(const std::vector<double>& lambdas, int n_categories, const std::vector<double>& prior_by_size, std::vector<int>& states)
@@ -364,6 +372,51 @@ reconstruction* cuda_gamma_model::reconstruct_ancestral_states(const std::vector
 }
 
 // ------------------------------------------------------------------------------------------------------
+
+// ------------------------------------------------------------------------------------------------------
+// p-values
+// ------------------------------------------------------------------------------------------------------
+
+std::vector<double> compute_pvalues_cuda(const clade* p_tree, const std::vector<gene_family>& families, const lambda* p_lambda,
+                                         const matrix_cache& cache, int number_of_simulations, int max_family_size, int max_root_family_size)
+{
+    const int mx = max_family_size, mxr = max_root_family_size, nsim = number_of_simulations;
+
+    // (1) simulate as get_random_probabilities does, root size by root size (src/probability.cpp:279-298): the calls
+    //     into randomizer_engine happen in the reference's order, so the simulated families are the reference's
+    std::vector<gene_family> sims((size_t)mxr * nsim);
+    for (int root_size = 0; root_size < mxr; ++root_size) {
+        for (int i = 0; i < nsim; ++i) {
+            clademap<int> sizes;
+            sizes[p_tree] = root_size;
+            auto fn = [&](const clade* c) { set_weighted_random_family_size(c, &sizes, p_lambda, nullptr, mx, cache); };
+            p_tree->apply_prefix_order(fn);
+            gene_family& fam = sims[(size_t)root_size * nsim + i];
+            for (auto& it : sizes)
+                if (it.first->is_leaf()) fam.set_species_size(it.first->get_taxon_name(), it.second);
+        }
+    }
+
+    // (2) likelihood of a family = max of its root vector (src/probability.cpp:308, 399): pruning kernel
+    auto likelihoods = [&](const std::vector<gene_family>& fams) {
+        cuda_bridge bridge(p_tree, mx, mxr);
+        bridge.bind(fams);
+        const std::vector<double> unique = bridge.root_max(bridge.lambda_table(p_lambda, std::vector<double>{1.0}));
+        std::vector<double> out(fams.size());
+        for (size_t i = 0; i < fams.size(); ++i) out[i] = unique[bridge.unique_of(i)];
+        return out;
+    };
+    const std::vector<double> cond = likelihoods(sims);
+    const std::vector<double> observed = likelihoods(families);
+
+    // (3) sort each conditional distribution, upper_bound, max over root sizes (src/probability.cpp:310, 379-409)
+    std::vector<double> result(families.size());
+    int device = 0;
+    if (const char* e = getenv("CAFE_B200_DEVICE")) device = atoi(e);
+    int rc = cafe_b200_pvalues(device, cond.data(), mxr, nsim, observed.data(), (int64_t)observed.size(), result.data());
+    if (rc != CAFE_B200_OK) throw std::runtime_error(std::string("cafe_b200_pvalues failed (") + std::to_string(rc) + "): " + cafe_b200_last_error(nullptr));
+    return result;
+}
 
 std::vector<model*> build_cuda_models(const input_parameters& user_input, user_data& user_data)
 {

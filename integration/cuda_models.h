@@ -63,6 +63,10 @@ public:
     long evaluate(const std::vector<double>& lambdas, const std::vector<double>& cat_probs, const std::vector<double>& prior, int mode,
                   std::vector<double>& family_lnl, std::vector<double>& cat_lk, std::vector<char>& failed);
 
+    //! max_j of the root vector of every UNIQUE family under one lambda set (no categories, no prior): the
+    //! likelihood compute_pvalues uses (src/probability.cpp:308, 399).
+    std::vector<double> root_max(const std::vector<double>& lambdas);
+
     //! Pupko reconstruction on the device: states[unique family][category][internal node].
     void reconstruct(const std::vector<double>& lambdas, int n_categories, const std::vector<double>& prior_by_size, std::vector<int>& states);
 
@@ -126,6 +130,14 @@ private:
 
     std::vector<double> cat_probs() const;
 };
+
+//! Drop-in for compute_pvalues (src/probability.cpp:411-444; caller src/execute.cpp:161).  The families are
+//! simulated on the host by the reference's own generator, in the reference's order (so the random stream, and
+//! therefore every simulated family, is the reference's); their likelihoods and the observed families'
+//! likelihoods come from the pruning kernel, the conditional distributions are sorted and searched on the device.
+class matrix_cache;
+std::vector<double> compute_pvalues_cuda(const clade* p_tree, const std::vector<gene_family>& families, const lambda* p_lambda,
+                                         const matrix_cache& cache, int number_of_simulations, int max_family_size, int max_root_family_size);
 
 //! Same decisions as build_models (src/core.cpp:16-50), instantiating the CUDA-backed subclasses.
 std::vector<model*> build_cuda_models(const input_parameters& user_input, user_data& user_data);

@@ -80,6 +80,11 @@ def lib():
         L.orc_reconstruct.argtypes = [C.POINTER(_Tree), _i32p, C.c_int64, C.c_int, _dp, C.c_int, C.c_int, _dp,
                                       C.c_int, C.c_int, _i32p]
         L.orc_weighted_averages.argtypes = [_i32p, C.c_int, C.c_int, _dp, _dp]
+        L.orc_root_max.restype = C.c_int
+        L.orc_root_max.argtypes = [C.POINTER(_Tree), _i32p, C.c_int64, C.c_int, _dp, C.c_int, C.c_int, C.c_int, _dp]
+        L.orc_pvalue.restype = C.c_double
+        L.orc_pvalue.argtypes = [C.c_double, _dp, C.c_int]
+        L.orc_pvalues.argtypes = [_dp, C.c_int, C.c_int, _dp, C.c_int64, _dp]
         L.orc_init()
         _lib = L
     return _lib
@@ -200,6 +205,28 @@ def reconstruct(flat, counts, lambdas, prior, mf, mrf):
     lib().orc_reconstruct(th.ref(), counts.ctypes.data_as(_i32p), F, nl, _d(lam), n_lambdas, k, _d(pr), mf, mrf,
                           states.ctypes.data_as(_i32p))
     return states
+
+
+def root_max(flat, counts, lambdas, mf, mrf):
+    """max_j of the root vector per family (src/probability.cpp:308, 399); lambdas: [n_lambdas] raw."""
+    th = TreeHandle(flat)
+    counts = np.ascontiguousarray(counts, np.int32)
+    F, nl = counts.shape
+    lam = np.ascontiguousarray(lambdas, np.float64).ravel()
+    out = np.zeros(F)
+    rc = lib().orc_root_max(th.ref(), counts.ctypes.data_as(_i32p), F, nl, _d(lam), lam.size, mf, mrf, _d(out))
+    if rc:
+        raise ValueError("count outside 0..max_family_size")
+    return out
+
+
+def pvalues(cond, observed):
+    """cond: [n_root_sizes][n_sim] unsorted simulated likelihoods; observed: [F].  src/probability.cpp:310, 379-409."""
+    cond = np.array(cond, np.float64, order="C", copy=True)
+    obs = np.ascontiguousarray(observed, np.float64)
+    out = np.zeros(len(obs))
+    lib().orc_pvalues(_d(cond), cond.shape[0], cond.shape[1], _d(obs), len(obs), _d(out))
+    return out
 
 
 def have_ref() -> bool:

@@ -569,3 +569,67 @@ void orc_weighted_averages(const int32_t* states, int k, int n_internal, const d
         out[v] = val;
     }
 }
+
+/* src/probability.cpp:301-308 (simulated families) and :396-399 (observed families): the likelihood both halves of
+ * compute_pvalues use is the plain maximum of the root vector — one lambda set, no categories, no prior. */
+int orc_root_max(const orc_tree* tree, const int32_t* counts, int64_t n_families, int n_leaves, const double* lambdas, int n_lambdas,
+                 int max_family_size, int max_root_family_size, double* out)
+{
+    orc_init();
+    int mf = max_family_size, mrf = max_root_family_size;
+    int n = (mrf > mf ? mrf : mf) + 1;
+    matset ms;
+    matset_build(&ms, tree, lambdas, n);
+    (void)n_lambdas;
+    size_t work_n = prune_work_doubles(tree, mf, mrf);
+    int error = 0;
+#pragma omp parallel
+    {
+        double* work = (double*)malloc(sizeof(double) * work_n);
+        double* root = (double*)malloc(sizeof(double) * (size_t)mrf);
+#pragma omp for schedule(dynamic, 16)
+        for (int64_t i = 0; i < n_families; ++i) {
+            if (prune_with(tree, &ms, counts + (size_t)i * n_leaves, NULL, 0, 0, mf, mrf, work, root)) { error = 1; out[i] = NAN; continue; }
+            double best = root[0];
+            for (int j = 1; j < mrf; ++j) if (best < root[j]) best = root[j];      /* std::max_element */
+            out[i] = best;
+        }
+        free(work); free(root);
+    }
+    matset_free(&ms);
+    return error ? -1 : 0;
+}
+
+static int cmp_double(const void* a, const void* b)
+{
+    double x = *(const double*)a, y = *(const double*)b;
+    return (x > y) - (x < y);
+}
+
+/* src/probability.cpp:379-389: idx = upper_bound(conddist, v) - begin, or size-1 when nothing is greater; idx / size */
+double orc_pvalue(double v, const double* sorted, int n)
+{
+    int lo = 0, hi = n;
+    while (lo < hi) {
+        int mid = (lo + hi) / 2;
+        if (sorted[mid] > v) hi = mid; else lo = mid + 1;
+    }
+    int idx = lo < n ? lo : n - 1;
+    return idx / (double)n;
+}
+
+/* src/probability.cpp:310 (sort of each conditional distribution) + :391-409 (max over root sizes) for every family.
+ * cond: [n_root_sizes][n_sim] unsorted, sorted IN PLACE. */
+void orc_pvalues(double* cond, int n_root_sizes, int n_sim, const double* observed, int64_t n_families, double* pvalues)
+{
+    for (int s = 0; s < n_root_sizes; ++s) qsort(cond + (size_t)s * n_sim, (size_t)n_sim, sizeof(double), cmp_double);
+    for (int64_t i = 0; i < n_families; ++i) {
+        double best = 0;
+        for (int s = 0; s < n_root_sizes; ++s) {
+            double pv = orc_pvalue(observed[i], cond + (size_t)s * n_sim, n_sim);
+            if (s == 0 || best < pv) best = pv;
+        }
+        pvalues[i] = best;
+    }
+}
+

@@ -92,6 +92,14 @@ int    orc_reconstruct(const orc_tree* tree, const int32_t* counts, int64_t n_fa
 /* src/gamma_core.cpp:282-299 */
 void   orc_weighted_averages(const int32_t* states, int k, int n_internal, const double* cat_probs, double* out);
 
+/* src/probability.cpp:301-308, :396-399: max of the root vector per family (one lambda set, no prior). */
+int    orc_root_max(const orc_tree* tree, const int32_t* counts, int64_t n_families, int n_leaves, const double* lambdas, int n_lambdas,
+                    int max_family_size, int max_root_family_size, double* out);
+/* src/probability.cpp:379-389 */
+double orc_pvalue(double v, const double* sorted, int n);
+/* src/probability.cpp:310 + :391-409; cond [n_root_sizes][n_sim] is sorted in place */
+void   orc_pvalues(double* cond, int n_root_sizes, int n_sim, const double* observed, int64_t n_families, double* pvalues);
+
 #ifdef __cplusplus
 }
 #endif

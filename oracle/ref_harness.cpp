@@ -20,6 +20,7 @@
 //   model::reconstruct_ancestral_states                     src/base_model.cpp:145, src/gamma_core.cpp:301
 //   optimizer::optimize                                     src/optimizer.cpp:539
 //   get_gamma                                               src/gamma.cpp:225
+//   compute_pvalues / set_weighted_random_family_size       src/probability.cpp:411 / :320
 #include <algorithm>
 #include <chrono>
 #include <cmath>
@@ -262,6 +263,88 @@ int cmd_prune(const args_t& a)
     return 0;
 }
 
+// compute_pvalues with a fixed seed.  The reference keeps the simulated families to itself, so after the call the
+// same random stream is replayed through the same reference functions (set_weighted_random_family_size,
+// compute_node_probability) to export what was simulated: leaf counts, unsorted conditional distributions, and the
+// observed families' likelihoods.  "replay_matches" says the replay reproduced the reference's p-values exactly.
+int cmd_pvalues(const args_t& a)
+{
+    setup s(a);
+    model* m = s.models[0];
+    const int nsim = (int)a.integer("nsim", 100);
+    const unsigned seed = (unsigned)a.integer("seed", 10);
+    const int mf = s.data.max_family_size, mrf = s.data.max_root_family_size;
+    const clade* tree = s.data.p_tree;
+    const lambda* lam = m->get_lambda();
+    matrix_cache cache(std::max(mrf, mf) + 1);
+    cache.precalculate_matrices(get_lambda_values(lam), tree->get_branch_lengths());
+
+    randomizer_engine.seed(seed);
+    auto t0 = std::chrono::steady_clock::now();
+    std::vector<double> pv;
+#ifdef WITH_CUDA_MODELS
+    if (a.integer("cuda", 0)) pv = compute_pvalues_cuda(tree, s.data.gene_families, lam, cache, nsim, mf, mrf);
+    else
+#endif
+    pv = compute_pvalues(tree, s.data.gene_families, lam, cache, nsim, mf, mrf);
+    double seconds = std::chrono::duration<double>(std::chrono::steady_clock::now() - t0).count();
+
+    // ---- replay
+    std::vector<const clade*> leaves;
+    for (auto c : s.order) if (c->is_leaf()) leaves.push_back(c);
+    std::vector<int> sim_counts((size_t)mrf * nsim * leaves.size());
+    std::vector<double> cond((size_t)mrf * nsim);
+    randomizer_engine.seed(seed);
+    for (int root_size = 0; root_size < mrf; ++root_size) {
+        std::vector<gene_family> fams(nsim);
+        for (int i = 0; i < nsim; ++i) {
+            clademap<int> sizes;
+            sizes[tree] = root_size;
+            auto fn = [&](const clade* c) { set_weighted_random_family_size(c, &sizes, lam, NULL, mf, cache); };
+            tree->apply_prefix_order(fn);
+            for (size_t l = 0; l < leaves.size(); ++l) {
+                fams[i].set_species_size(leaves[l]->get_taxon_name(), sizes.at(leaves[l]));
+                sim_counts[((size_t)root_size * nsim + i) * leaves.size() + l] = sizes.at(leaves[l]);
+            }
+        }
+        for (int i = 0; i < nsim; ++i) {
+            clademap<std::vector<double>> pruner;
+            tree->apply_reverse_level_order([&](const clade* node) { pruner[node].resize(node->is_root() ? mrf : mf + 1); });
+            tree->apply_reverse_level_order([&](const clade* c) { compute_node_probability(c, fams[i], NULL, pruner, mrf, mf, lam, cache); });
+            cond[(size_t)root_size * nsim + i] = *std::max_element(pruner.at(tree).begin(), pruner.at(tree).end());
+        }
+    }
+    std::vector<double> observed(s.data.gene_families.size());
+    for (size_t f = 0; f < observed.size(); ++f) {
+        clademap<std::vector<double>> pruner;
+        tree->apply_reverse_level_order([&](const clade* node) { pruner[node].resize(node->is_root() ? mrf : mf + 1); });
+        tree->apply_reverse_level_order([&](const clade* c) { compute_node_probability(c, s.data.gene_families[f], NULL, pruner, mrf, mf, lam, cache); });
+        observed[f] = *std::max_element(pruner.at(tree).begin(), pruner.at(tree).end());
+    }
+    bool same = true;
+    {
+        std::vector<std::vector<double>> sorted(mrf);
+        for (int r = 0; r < mrf; ++r) { sorted[r].assign(cond.begin() + (size_t)r * nsim, cond.begin() + (size_t)(r + 1) * nsim); std::sort(sorted[r].begin(), sorted[r].end()); }
+        for (size_t f = 0; f < observed.size(); ++f) {
+            double best = 0;
+            for (int r = 0; r < mrf; ++r) best = std::max(best, pvalue(observed[f], sorted[r]));
+            if (best != pv[f]) same = false;
+        }
+    }
+    dumper d(a.str("dump"));
+    d.ints(sim_counts.data(), sim_counts.size());
+    d.doubles(cond.data(), cond.size());
+    d.doubles(observed.data(), observed.size());
+    d.doubles(pv.data(), pv.size());
+    printf("{"); print_setup(s);
+    printf("\"nsim\": %d, \"seed\": %u, \"n_leaves\": %zu, \"seconds\": %.6f, \"replay_matches\": %s, \"leaf_order\": [", nsim, seed, leaves.size(), seconds, same ? "true" : "false");
+    for (size_t l = 0; l < leaves.size(); ++l) printf("%s\"%s\"", l ? ", " : "", leaves[l]->get_taxon_name().c_str());
+    printf("]");
+    if (pv.size() <= 16) { printf(", "); jarr("pvalues", pv); }
+    printf("}\n");
+    return 0;
+}
+
 // One (or --reps) model::infer_family_likelihoods; optional reconstruction.
 int cmd_eval(const args_t& a)
 {
@@ -379,6 +462,7 @@ int main(int argc, char** argv)
         if (cmd == "poisson") return cmd_poisson(a);
         if (cmd == "prune") return cmd_prune(a);
         if (cmd == "eval") return cmd_eval(a);
+        if (cmd == "pvalues") return cmd_pvalues(a);
         if (cmd == "fit") return cmd_fit(a);
         fprintf(stderr, "unknown command %s\n", cmd.c_str());
         return 2;

@@ -223,6 +223,30 @@ def mammal_outputs(tmp, flat, ids, counts):
     np.savez_compressed(os.path.join(GOLD, "mammal_outputs.npz"), meta=json.dumps(meta), keep=np.flatnonzero(keep).astype(np.int32), **store)
 
 
+def pvalues(tmp):
+    """compute_pvalues (src/probability.cpp:411-444) on the first 300 root-filtered mammal families, 50 simulations per
+    root size, seed 10: the simulated leaf counts, their likelihoods (unsorted conditional distributions), the observed
+    families' likelihoods and the reference's p-values."""
+    E = {"tree": os.path.join(EX, "mammals_tree.txt"), "fam": os.path.join(EX, "mammal_gene_families.txt")}
+    limit, nsim, seed, lam = 300, 50, 10, 0.002
+    dump = os.path.join(tmp, "pv.bin")
+    r = orc.run_ref("pvalues", dump=dump, limit=limit, nsim=nsim, seed=seed, **E, **{"lambda": lam})
+    assert r["replay_matches"] is True
+    mrf, nl, F = r["max_root_family_size"], r["n_leaves"], r["n_families"]
+    raw = open(dump, "rb").read()
+    o = 0
+    sim = np.frombuffer(raw, np.int32, mrf * nsim * nl, o).reshape(mrf * nsim, nl); o += sim.nbytes
+    cond = np.frombuffer(raw, np.float64, mrf * nsim, o).reshape(mrf, nsim); o += cond.nbytes
+    obs = np.frombuffer(raw, np.float64, F, o); o += obs.nbytes
+    pv = np.frombuffer(raw, np.float64, F, o); o += pv.nbytes
+    assert o == len(raw) and sim.max() < 256
+    meta = {"limit": limit, "nsim": nsim, "seed": seed, "lambda": lam, "max_family_size": r["max_family_size"],
+            "max_root_family_size": mrf, "leaf_order": r["leaf_order"]}
+    np.savez_compressed(os.path.join(GOLD, "mammal_pvalues.npz"), meta=json.dumps(meta), sim_counts=sim.astype(np.uint8), cond=cond,
+                        observed=obs, pvalues=pv)
+    print("pvalues", F, "families,", mrf * nsim, "simulated;", np.unique(pv).size, "distinct p-values", flush=True)
+
+
 def fits():
     E = {"tree": os.path.join(EX, "mammals_tree.txt"), "fam": os.path.join(EX, "mammal_gene_families.txt")}
     path = os.path.join(GOLD, "fits.json")
@@ -253,7 +277,7 @@ def main():
         raise SystemExit("oracle/_ref/ref_harness missing: run `make -C oracle ref` (needs /root/reference)")
     os.makedirs(GOLD, exist_ok=True)
     with tempfile.TemporaryDirectory() as tmp:
-        steps = args.only.split(",") if args.only else ["inputs", "scalars", "matrices", "unit", "mammal"]
+        steps = args.only.split(",") if args.only else ["inputs", "scalars", "matrices", "unit", "mammal", "pvalues"]
         flat = ids = counts = None
         if "inputs" in steps or "mammal" in steps:
             flat, ids, counts = mammal_inputs()
@@ -265,6 +289,8 @@ def main():
             unit_fixtures(tmp)
         if "mammal" in steps:
             mammal_outputs(tmp, flat, ids, counts)
+        if "pvalues" in steps:
+            pvalues(tmp)
         if args.fits:
             fits()
 
