@@ -8,6 +8,7 @@
 #include "../../include/cafe_b200.h"
 
 #include <algorithm>
+#include <climits>
 #include <cmath>
 #include <cstdio>
 #include <cstring>
@@ -778,17 +779,25 @@ int cafe_b200_create(cafe_b200_ctx** out, const cafe_b200_tree* tree, const int3
 int cafe_b200_set_families(cafe_b200_ctx* c, const int32_t* leaf_counts, int64_t n_families)
 {
     if (!c || !leaf_counts || n_families != c->n_families) return fail(c, CAFE_B200_ERR_ARG, "set_families: shape must match create");
-    int mx = 0;
     const int64_t total = n_families * c->n_leaves;
-    for (int64_t i = 0; i < total; ++i) {
-        if (leaf_counts[i] < 0) return fail(c, CAFE_B200_ERR_COUNT_RANGE, "negative leaf count");
-        mx = std::max(mx, (int)leaf_counts[i]);
-    }
-    if (mx > c->mf) return fail(c, CAFE_B200_ERR_COUNT_RANGE, "a leaf count exceeds max_family_size");
+    if (total == 0) return CAFE_B200_OK;
     CUDA_TRY(c, cudaSetDevice(c->device));
+    // upload, then range-check on the device (a host pass over 10^8 counts costs more than the copy)
+    int* d_range = reinterpret_cast<int*>(c->d_partial);      // scratch: [min, max]
+    const int init[2] = {INT_MAX, INT_MIN};
+    CUDA_TRY(c, cudaMemcpyAsync(d_range, init, sizeof(init), cudaMemcpyHostToDevice, c->stream));
     CUDA_TRY(c, cudaMemcpyAsync(c->d_counts, leaf_counts, (size_t)total * sizeof(int32_t), cudaMemcpyHostToDevice, c->stream));
+    const int blocks = (int)std::max<int64_t>(1, std::min<int64_t>((total / 4 + RED_THREADS - 1) / RED_THREADS, 8 * (int64_t)c->sm_count));
+    count_range_kernel<<<blocks, RED_THREADS, 0, c->stream>>>(c->d_counts, total, d_range);
+    CUDA_TRY(c, cudaGetLastError());
+    c->launches++;
+    int range[2] = {0, 0};
+    CUDA_TRY(c, cudaMemcpyAsync(range, d_range, sizeof(range), cudaMemcpyDeviceToHost, c->stream));
     CUDA_TRY(c, cudaStreamSynchronize(c->stream));
-    c->max_count = mx;
+    // the context now holds the new matrix; out-of-range counts are refused here and again by every evaluation
+    c->max_count = range[1];
+    if (range[0] < 0) { c->max_count = c->mf + 1; return fail(c, CAFE_B200_ERR_COUNT_RANGE, "negative leaf count"); }
+    if (range[1] > c->mf) return fail(c, CAFE_B200_ERR_COUNT_RANGE, "a leaf count exceeds max_family_size");
     return CAFE_B200_OK;
 }
 

@@ -11,6 +11,8 @@
 // Bound: HBM (reads k doubles + k flags, writes one double per family) — a few MB, latency-sized.
 #pragma once
 
+#include <climits>
+
 #include "common.cuh"
 
 namespace cafe {
@@ -74,6 +76,34 @@ __global__ void __launch_bounds__(RED_THREADS) final_sum_kernel(int n_partials, 
         __syncthreads();
     }
     if (threadIdx.x == 0) { result[0] = s_sum[0]; result[1] = s_bad[0]; }
+}
+
+// Range check of an uploaded count matrix (cafe_b200_set_families): range[0] = min, range[1] = max over all
+// leaf counts, so that the reference's out-of-range indexing (src/probability.cpp:191,197) is refused without a
+// host pass over the matrix.  Bound: HBM — 4 B per count, 16-byte vector loads, grid-stride.
+__global__ void __launch_bounds__(RED_THREADS) count_range_kernel(const int32_t* __restrict__ counts, int64_t n, int* __restrict__ range)
+{
+    int lo = INT_MAX, hi = INT_MIN;
+    const int64_t n4 = n / 4;
+    const int4* c4 = reinterpret_cast<const int4*>(counts);
+    for (int64_t i = (int64_t)blockIdx.x * RED_THREADS + threadIdx.x; i < n4; i += (int64_t)gridDim.x * RED_THREADS) {
+        const int4 v = __ldg(c4 + i);
+        lo = min(lo, min(min(v.x, v.y), min(v.z, v.w)));
+        hi = max(hi, max(max(v.x, v.y), max(v.z, v.w)));
+    }
+    for (int64_t i = n4 * 4 + (int64_t)blockIdx.x * RED_THREADS + threadIdx.x; i < n; i += (int64_t)gridDim.x * RED_THREADS) {
+        lo = min(lo, counts[i]);
+        hi = max(hi, counts[i]);
+    }
+    #pragma unroll
+    for (int off = 16; off > 0; off >>= 1) {
+        lo = min(lo, __shfl_xor_sync(0xffffffffu, lo, off));
+        hi = max(hi, __shfl_xor_sync(0xffffffffu, hi, off));
+    }
+    if ((threadIdx.x & 31) == 0) {
+        atomicMin(&range[0], lo);
+        atomicMax(&range[1], hi);
+    }
 }
 
 }  // namespace cafe

@@ -95,7 +95,9 @@ int  cafe_b200_create(cafe_b200_ctx** out, const cafe_b200_tree* tree, const int
 void cafe_b200_destroy(cafe_b200_ctx* ctx);
 const char* cafe_b200_last_error(const cafe_b200_ctx* ctx);   /* ctx may be NULL: last create() error */
 
-/* Re-upload the count matrix (same shape as at create).  Replaces model::set_families (src/core.h:148). */
+/* Re-upload the count matrix (same shape as at create).  Replaces model::set_families (src/core.h:148).
+ * The range check (0 <= count <= max_family_size) runs on the device after the copy: on CAFE_B200_ERR_COUNT_RANGE
+ * the context holds the rejected matrix and refuses every evaluation until a valid one is set. */
 int  cafe_b200_set_families(cafe_b200_ctx* ctx, const int32_t* leaf_counts, int64_t n_families);
 
 /* Leaf error model: dense HOST [rows][n_deviations] table indexed by OBSERVED count, i.e. row s =

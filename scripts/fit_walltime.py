@@ -1,0 +1,71 @@
+#!/usr/bin/env python
+"""Second half of BASELINE.json's metric: wall time of a full ML fit (and of the p-value phase) on the mammal set.
+
+Runs the reference's own host code (optimizer::optimize, seed 10) twice on this box: over the reference's CPU models
+(oracle/_ref/ref_harness) and over the CUDA-backed models of integration/cuda_models.cpp (oracle/_ref/ref_harness_cuda).
+TEST / MEASUREMENT INFRASTRUCTURE: both binaries link the unmodified reference objects and live under oracle/_ref/.
+Prints one JSON object; the committed copy is profiles/r01_fit_walltime.json.
+
+    python scripts/fit_walltime.py [--cpu-gamma]        (the gamma CPU fit takes ~15 min on 8 threads; off by default)
+"""
+import argparse
+import json
+import os
+import subprocess
+import sys
+import tempfile
+import time
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+sys.path.insert(0, ROOT)
+from cafexp_b200 import hostio  # noqa: E402
+
+GOLD = os.path.join(ROOT, "tests", "golden")
+
+
+def run(binary, cmd, cuda, **kw):
+    argv = [os.path.join(ROOT, "oracle", "_ref", binary), cmd]
+    if cuda:
+        argv += ["--cuda", "1"]
+    for k, v in kw.items():
+        argv += ["--" + k, repr(v) if isinstance(v, float) else str(v)]
+    t0 = time.perf_counter()
+    res = subprocess.run(argv, capture_output=True, text=True, check=True)
+    wall = time.perf_counter() - t0
+    d = json.loads([l for l in res.stdout.splitlines() if l.startswith("{\"")][-1])
+    d.pop("node_order", None)
+    d.pop("leaf_order", None)
+    d["process_wall_s"] = round(wall, 3)
+    return d
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--cpu-gamma", action="store_true")
+    ap.add_argument("--pvalue-families", type=int, default=2000)
+    ap.add_argument("--nsim", type=int, default=1000)
+    args = ap.parse_args()
+    inp = json.load(open(os.path.join(GOLD, "mammal_inputs.json")))
+    flat = hostio.flatten_tree(hostio.parse_newick(inp["tree"]))
+    z = np.load(os.path.join(GOLD, "mammal_counts.npz"))
+    out = {"host_cores": os.cpu_count(), "workload": "examples/mammal_gene_families.txt + mammals_tree.txt (10 956 root-filtered families, N=141), seed 10"}
+    with tempfile.TemporaryDirectory() as tmp:
+        tree, fam = os.path.join(tmp, "tree.txt"), os.path.join(tmp, "fam.txt")
+        open(tree, "w").write(inp["tree"] + "\n")
+        hostio.write_gene_families(fam, flat, [str(i) for i in z["ids"]], z["counts"].astype(np.int32))
+        E = {"tree": tree, "fam": fam, "seed": 10}
+        out["fit_single_lambda_cuda"] = run("ref_harness_cuda", "fit", True, **E)
+        out["fit_gamma4_lambda_alpha_cuda"] = run("ref_harness_cuda", "fit", True, k=4, **E)
+        out["fit_single_lambda_cpu_reference"] = run("ref_harness", "fit", False, **E)
+        if args.cpu_gamma:
+            out["fit_gamma4_lambda_alpha_cpu_reference"] = run("ref_harness", "fit", False, k=4, **E)
+        P = dict(E, limit=args.pvalue_families, nsim=args.nsim, **{"lambda": 0.002})
+        out["pvalues_cuda"] = run("ref_harness_cuda", "pvalues", True, **P)
+        out["pvalues_cpu_reference"] = run("ref_harness", "pvalues", False, **P)
+    print(json.dumps(out, indent=1))
+
+
+if __name__ == "__main__":
+    main()

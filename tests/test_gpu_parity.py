@@ -276,6 +276,16 @@ def test_edge_cases():
         # count above max_family_size is rejected like an out-of-range index would be
         with pytest.raises(engine.CafeB200Error, match="COUNT_RANGE"):
             eng.set_families(np.array([[0, 0, 0, 26]] * 3, np.int32))
+        # the rejected matrix is on the device (the check runs there): evaluations are refused until a valid one is set
+        with pytest.raises(engine.CafeB200Error, match="COUNT_RANGE"):
+            eng.infer([[0.03]], prior)
+        with pytest.raises(engine.CafeB200Error, match="COUNT_RANGE"):
+            eng.set_families(np.array([[0, 0, 0, -1]] * 3, np.int32))
+        with pytest.raises(engine.CafeB200Error, match="COUNT_RANGE"):
+            eng.infer([[0.03]], prior)
+        eng.set_families(counts)
+        again = eng.infer([[0.03]], prior)
+        assert np.array_equal(again["family_lnl"], got["family_lnl"], equal_nan=True)
     with pytest.raises(engine.CafeB200Error, match="COUNT_RANGE"):
         engine.Engine(tree, np.array([[0, 0, 0, 26]], np.int32), 25, 20)
     # mrf > mf exercises N = max(mrf, mf) + 1
@@ -294,7 +304,7 @@ def test_set_families_and_launch_accounting(mammal):
         assert n1 == 4                                # matrix build, prune, finalize, final sum
         eng.set_families(counts[::-1].copy())
         b = eng.infer([[0.002]], prior)
-        assert eng.launches == 8
+        assert eng.launches == 9                      # + the device-side range check of the uploaded counts
         assert np.array_equal(b["family_lnl"], a["family_lnl"][::-1])
         t = eng.last_timings_ms()
         assert t["prune"] > 0 and t["matrix_build"] > 0
