@@ -289,6 +289,11 @@ int cmd_pvalues(const args_t& a)
     pv = compute_pvalues(tree, s.data.gene_families, lam, cache, nsim, mf, mrf);
     double seconds = std::chrono::duration<double>(std::chrono::steady_clock::now() - t0).count();
 
+    if (a.integer("replay", 1) == 0) {       // timing runs: skip the (serial, CPU) replay
+        printf("{"); print_setup(s);
+        printf("\"nsim\": %d, \"seed\": %u, \"seconds\": %.6f}\n", nsim, seed, seconds);
+        return 0;
+    }
     // ---- replay
     std::vector<const clade*> leaves;
     for (auto c : s.order) if (c->is_leaf()) leaves.push_back(c);

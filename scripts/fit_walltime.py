@@ -61,7 +61,7 @@ def main():
         out["fit_single_lambda_cpu_reference"] = run("ref_harness", "fit", False, **E)
         if args.cpu_gamma:
             out["fit_gamma4_lambda_alpha_cpu_reference"] = run("ref_harness", "fit", False, k=4, **E)
-        P = dict(E, limit=args.pvalue_families, nsim=args.nsim, **{"lambda": 0.002})
+        P = dict(E, limit=args.pvalue_families, nsim=args.nsim, replay=0, **{"lambda": 0.002})
         out["pvalues_cuda"] = run("ref_harness_cuda", "pvalues", True, **P)
         out["pvalues_cpu_reference"] = run("ref_harness", "pvalues", False, **P)
     print(json.dumps(out, indent=1))
