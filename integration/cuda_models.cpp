@@ -5,6 +5,7 @@
 #include <algorithm>
 #include <cmath>
 #include <numeric>
+#include <random>
 #include <stdexcept>
 #include <unordered_map>
 
@@ -21,6 +22,8 @@
 #include "root_distribution.h"
 #include "root_equilibrium_distribution.h"
 #include "user_data.h"
+
+extern std::mt19937 randomizer_engine;      // the reference's generator (main.cpp)
 
 namespace {
 
@@ -93,7 +96,20 @@ void cuda_bridge::check(int rc, const char* what) const
 void cuda_bridge::bind(const std::vector<gene_family>& families)
 {
     if (_ctx && _bound == &families && _bound_size == families.size()) return;
+    const size_t nl = _leaves.size();
+    std::vector<int> rows(families.size() * nl);
+    for (size_t i = 0; i < families.size(); ++i)
+        for (size_t l = 0; l < nl; ++l) rows[i * nl + l] = families[i].get_species_size(_leaves[l]->get_taxon_name());
+    bind_rows(rows, families.size());
+    _bound = &families;
+    _bound_size = families.size();
+}
+
+void cuda_bridge::bind_rows(const std::vector<int>& rows, size_t n_rows)
+{
     if (_ctx) { cafe_b200_destroy(_ctx); _ctx = nullptr; }
+    _bound = nullptr;
+    _bound_size = 0;
 
     // Identical count rows are evaluated once.  The reference does this for the base model only
     // (build_reference_list, src/base_model.cpp:27-51, O(F^2)); identical inputs give identical outputs for
@@ -101,11 +117,11 @@ void cuda_bridge::bind(const std::vector<gene_family>& families)
     const size_t nl = _leaves.size();
     std::unordered_map<std::vector<int>, size_t, count_row_hash> seen;
     std::vector<int32_t> counts;
-    _unique_of.resize(families.size());
+    _unique_of.resize(n_rows);
     _max_count = 0;
     std::vector<int> row(nl);
-    for (size_t i = 0; i < families.size(); ++i) {
-        for (size_t l = 0; l < nl; ++l) row[l] = families[i].get_species_size(_leaves[l]->get_taxon_name());
+    for (size_t i = 0; i < n_rows; ++i) {
+        row.assign(rows.begin() + i * nl, rows.begin() + (i + 1) * nl);
         auto it = seen.find(row);
         if (it == seen.end()) {
             it = seen.emplace(row, seen.size()).first;
@@ -131,8 +147,6 @@ void cuda_bridge::bind(const std::vector<gene_family>& families)
         _ctx = nullptr;
         throw std::runtime_error(std::string("cafe_b200_create failed (") + std::to_string(rc) + "): " + cafe_b200_last_error(nullptr));
     }
-    _bound = &families;
-    _bound_size = families.size();
 }
 
 void cuda_bridge::set_error_model(const error_model* p_error_model)
@@ -382,32 +396,80 @@ std::vector<double> compute_pvalues_cuda(const clade* p_tree, const std::vector<
 {
     const int mx = max_family_size, mxr = max_root_family_size, nsim = number_of_simulations;
 
-    // (1) simulate as get_random_probabilities does, root size by root size (src/probability.cpp:279-298): the calls
-    //     into randomizer_engine happen in the reference's order, so the simulated families are the reference's
-    std::vector<gene_family> sims((size_t)mxr * nsim);
+    // (1) simulate as get_random_probabilities does, root size by root size (src/probability.cpp:279-298), drawing from
+    //     randomizer_engine in the reference's order with the reference's distributions, so every simulated family is
+    //     the reference's.  What set_weighted_random_family_size (src/probability.cpp:320-351) rebuilds per call — the
+    //     weight vector of row `parent size` and its std::discrete_distribution — depends only on (edge, parent size)
+    //     and is built once here; a distribution object draws the same values however often it is reused.
+    std::vector<const clade*> prefix;
+    p_tree->apply_prefix_order([&](const clade* c) { prefix.push_back(c); });
+    std::map<const clade*, int> pos;
+    for (size_t i = 0; i < prefix.size(); ++i) pos[prefix[i]] = (int)i;
+    struct edge_sampler {
+        int parent = -1;
+        int leaf_col = -1;
+        bool saturated = false;
+        const matrix* probabilities = nullptr;
+        std::vector<std::unique_ptr<std::discrete_distribution<int>>> by_parent_size;
+    };
+    cuda_bridge sim_bridge(p_tree, mx, mxr);
+    const std::vector<const clade*>& leaves = sim_bridge.leaf_nodes();
+    std::vector<edge_sampler> edge(prefix.size());
+    for (size_t i = 0; i < prefix.size(); ++i) {
+        const clade* c = prefix[i];
+        if (c->is_root()) continue;
+        edge[i].parent = pos.at(c->get_parent());
+        const double lam = p_lambda->get_value_for_clade(c), t = c->get_branch_length();
+        edge[i].probabilities = cache.get_matrix(t, lam);
+        edge[i].saturated = cache.is_saturated(t, lam);
+        edge[i].by_parent_size.resize(edge[i].probabilities->size());
+        if (c->is_leaf()) edge[i].leaf_col = (int)(std::find(leaves.begin(), leaves.end(), c) - leaves.begin());
+    }
+    const size_t nl = leaves.size();
+    std::vector<int> sim_rows((size_t)mxr * nsim * nl, 0);
+    std::vector<int> sizes(prefix.size());
+    std::vector<double> v(mx);
     for (int root_size = 0; root_size < mxr; ++root_size) {
         for (int i = 0; i < nsim; ++i) {
-            clademap<int> sizes;
-            sizes[p_tree] = root_size;
-            auto fn = [&](const clade* c) { set_weighted_random_family_size(c, &sizes, p_lambda, nullptr, mx, cache); };
-            p_tree->apply_prefix_order(fn);
-            gene_family& fam = sims[(size_t)root_size * nsim + i];
-            for (auto& it : sizes)
-                if (it.first->is_leaf()) fam.set_species_size(it.first->get_taxon_name(), it.second);
+            int* row = &sim_rows[((size_t)root_size * nsim + i) * nl];
+            for (size_t n = 0; n < prefix.size(); ++n) {
+                edge_sampler& e = edge[n];
+                if (e.parent < 0) { sizes[n] = root_size; continue; }
+                const int parent_size = sizes[e.parent];
+                int c = 0;
+                if (parent_size > 0) {
+                    if (e.saturated) {
+                        std::uniform_int_distribution<int> distribution(0, mx - 1);      // drawn and overwritten, as in the reference
+                        c = distribution(randomizer_engine);
+                    }
+                    auto& dist = e.by_parent_size[parent_size];
+                    if (!dist) {
+                        for (int k = 0; k < mx; ++k) v[k] = e.probabilities->get(parent_size, k);
+                        dist.reset(new std::discrete_distribution<int>(v.begin(), v.end()));
+                    }
+                    c = (*dist)(randomizer_engine);
+                }
+                sizes[n] = c;
+                if (e.leaf_col >= 0) row[e.leaf_col] = c;
+            }
         }
     }
 
     // (2) likelihood of a family = max of its root vector (src/probability.cpp:308, 399): pruning kernel
-    auto likelihoods = [&](const std::vector<gene_family>& fams) {
+    const std::vector<double> lambdas = sim_bridge.lambda_table(p_lambda, std::vector<double>{1.0});
+    sim_bridge.bind_rows(sim_rows, (size_t)mxr * nsim);
+    std::vector<double> cond((size_t)mxr * nsim);
+    {
+        const std::vector<double> unique = sim_bridge.root_max(lambdas);
+        for (size_t i = 0; i < cond.size(); ++i) cond[i] = unique[sim_bridge.unique_of(i)];
+    }
+    std::vector<double> observed(families.size());
+    {
         cuda_bridge bridge(p_tree, mx, mxr);
-        bridge.bind(fams);
-        const std::vector<double> unique = bridge.root_max(bridge.lambda_table(p_lambda, std::vector<double>{1.0}));
-        std::vector<double> out(fams.size());
-        for (size_t i = 0; i < fams.size(); ++i) out[i] = unique[bridge.unique_of(i)];
-        return out;
-    };
-    const std::vector<double> cond = likelihoods(sims);
-    const std::vector<double> observed = likelihoods(families);
+        bridge.bind(families);
+        const std::vector<double> unique = bridge.root_max(lambdas);
+        for (size_t i = 0; i < observed.size(); ++i) observed[i] = unique[bridge.unique_of(i)];
+    }
 
     // (3) sort each conditional distribution, upper_bound, max over root sizes (src/probability.cpp:310, 379-409)
     std::vector<double> result(families.size());

@@ -49,6 +49,9 @@ public:
     //! (Re)creates the device context if `families` is not the vector the current one was built from.
     void bind(const std::vector<gene_family>& families);
 
+    //! Same for raw count rows [n_rows][leaves in leaf_nodes() order] (simulated families never become gene_family objects).
+    void bind_rows(const std::vector<int>& rows, size_t n_rows);
+
     //! Uploads the error model as a dense [observed count][deviation] table (or removes it).
     void set_error_model(const error_model* p_error_model);
 
@@ -74,6 +77,7 @@ public:
     size_t unique_count() const { return _n_unique; }
     int node_count() const { return (int)_order.size(); }
     const std::vector<const clade*>& internal_nodes() const { return _internal; }
+    const std::vector<const clade*>& leaf_nodes() const { return _leaves; }       // = count-matrix columns
     int max_family_size() const { return _mf; }
     int max_root_family_size() const { return _mrf; }
 

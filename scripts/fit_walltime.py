@@ -56,6 +56,7 @@ def main():
         open(tree, "w").write(inp["tree"] + "\n")
         hostio.write_gene_families(fam, flat, [str(i) for i in z["ids"]], z["counts"].astype(np.int32))
         E = {"tree": tree, "fam": fam, "seed": 10}
+        run("ref_harness_cuda", "eval", True, tree=tree, fam=fam, limit=64, **{"lambda": 0.002})     # untimed: first CUDA process on the box
         out["fit_single_lambda_cuda"] = run("ref_harness_cuda", "fit", True, **E)
         out["fit_gamma4_lambda_alpha_cuda"] = run("ref_harness_cuda", "fit", True, k=4, **E)
         out["fit_single_lambda_cpu_reference"] = run("ref_harness", "fit", False, **E)
