@@ -23,6 +23,7 @@
 #include "pupko.cuh"
 #include "pvalue.cuh"
 #include "reduce.cuh"
+#include "viterbi.cuh"
 
 using namespace cafe;
 
@@ -992,6 +993,44 @@ int cafe_b200_pvalues(int device, const double* cond, int n_root_sizes, int n_si
     if (e == cudaSuccess) e = cudaMemcpy(pvalues, d_p, (size_t)n_families * sizeof(double), cudaMemcpyDeviceToHost);
     cudaFree(d_cond); cudaFree(d_obs); cudaFree(d_p);
     if (e != cudaSuccess) return fail(nullptr, CAFE_B200_ERR_CUDA, std::string("pvalues: ") + cudaGetErrorString(e));
+    return CAFE_B200_OK;
+}
+
+int cafe_b200_branch_probabilities(cafe_b200_ctx* c, const double* lambdas, int n_lambdas, const int32_t* node_sizes, const uint8_t* selected,
+                                   double* out)
+{
+    if (!c || !lambdas || !node_sizes || !out) return fail(c, CAFE_B200_ERR_ARG, "bad argument to branch_probabilities");
+    if (c->n_families == 0) return CAFE_B200_OK;
+    const int nn = c->tree.n_nodes;
+    const size_t total = (size_t)c->n_families * nn;
+    const int hi = std::min(c->mf, c->n - 1);
+    for (size_t i = 0; i < total; ++i)
+        if (node_sizes[i] < 0 || node_sizes[i] > hi) return fail(c, CAFE_B200_ERR_COUNT_RANGE, "a node size is outside 0..max_family_size");
+    CUDA_TRY(c, cudaSetDevice(c->device));
+    std::vector<double> ones(c->n, 1.0);
+    const double cp = 1.0;
+    int rc = stage_and_build(c, lambdas, n_lambdas, 1, &cp, ones.data(), c->n);
+    if (rc) return rc;
+    int32_t* d_sizes = nullptr;
+    uint8_t* d_sel = nullptr;
+    double* d_out = nullptr;
+    cudaError_t e = dev_alloc(&d_sizes, total);
+    if (e == cudaSuccess) e = dev_alloc(&d_out, total);
+    if (e == cudaSuccess && selected) e = dev_alloc(&d_sel, (size_t)c->n_families);
+    if (e == cudaSuccess) e = cudaMemcpyAsync(d_sizes, node_sizes, total * sizeof(int32_t), cudaMemcpyHostToDevice, c->stream);
+    if (e == cudaSuccess && selected) e = cudaMemcpyAsync(d_sel, selected, (size_t)c->n_families, cudaMemcpyHostToDevice, c->stream);
+    if (e == cudaSuccess) {
+        const int blocks = (int)((total + VT_THREADS - 1) / VT_THREADS);
+        viterbi_kernel<<<blocks, VT_THREADS, 0, c->stream>>>(c->n_families, nn, c->mf, c->nr, c->d_parent, c->d_mat_of, c->d_mt, c->mt_stride, d_sizes,
+                                                              d_sel, d_out);
+        e = cudaGetLastError();
+        c->launches++;
+    }
+    if (e == cudaSuccess) e = cudaMemcpyAsync(out, d_out, total * sizeof(double), cudaMemcpyDeviceToHost, c->stream);
+    if (e == cudaSuccess) e = cudaStreamSynchronize(c->stream);
+    cudaStreamSynchronize(c->stream);
+    cudaFree(d_sizes); cudaFree(d_sel); cudaFree(d_out);
+    if (e != cudaSuccess) return fail(c, CAFE_B200_ERR_CUDA, std::string("branch_probabilities: ") + cudaGetErrorString(e));
     return CAFE_B200_OK;
 }
 

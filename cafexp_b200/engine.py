@@ -28,6 +28,7 @@ EXPORTS = [
     "cafe_b200_last_error", "cafe_b200_set_families", "cafe_b200_set_error_model", "cafe_b200_set_option", "cafe_b200_set_stream",
     "cafe_b200_eval", "cafe_b200_eval_device", "cafe_b200_reconstruct", "cafe_b200_build_matrices", "cafe_b200_matrix_size",
     "cafe_b200_prune_roots", "cafe_b200_launch_count", "cafe_b200_last_timings", "cafe_b200_root_max", "cafe_b200_pvalues",
+    "cafe_b200_branch_probabilities",
 ]
 
 _dp = C.POINTER(C.c_double)
@@ -93,6 +94,8 @@ def load_library():
     L.cafe_b200_root_max.argtypes = [C.c_void_p, _dp, C.c_int, _dp]
     L.cafe_b200_pvalues.restype = C.c_int
     L.cafe_b200_pvalues.argtypes = [C.c_int, _dp, C.c_int, C.c_int, _dp, C.c_int64, _dp]
+    L.cafe_b200_branch_probabilities.restype = C.c_int
+    L.cafe_b200_branch_probabilities.argtypes = [C.c_void_p, _dp, C.c_int, _i32p, C.POINTER(C.c_uint8), _dp]
     L.cafe_b200_launch_count.restype = C.c_int64
     L.cafe_b200_launch_count.argtypes = [C.c_void_p]
     L.cafe_b200_last_timings.restype = C.c_int
@@ -235,6 +238,18 @@ class Engine:
         lam = np.ascontiguousarray(lambdas, np.float64).ravel()
         out = np.zeros(self.n_families)
         self._check(self._lib.cafe_b200_root_max(self._h, _d(lam), lam.size, _d(out)), "cafe_b200_root_max")
+        return out
+
+    def branch_probabilities(self, lambdas, node_sizes, selected=None):
+        """compute_viterbi_sum for every (family, node) (cafe_b200_branch_probabilities); -1 where the reference has no value."""
+        lam = np.ascontiguousarray(lambdas, np.float64).ravel()
+        sizes = np.ascontiguousarray(node_sizes, np.int32)
+        assert sizes.shape == (self.n_families, self.tree.n_nodes)
+        sel = None if selected is None else np.ascontiguousarray(selected, np.uint8)
+        out = np.empty((self.n_families, self.tree.n_nodes))
+        self._check(self._lib.cafe_b200_branch_probabilities(self._h, _d(lam), lam.size, sizes.ctypes.data_as(_i32p),
+                                                             None if sel is None else sel.ctypes.data_as(C.POINTER(C.c_uint8)), _d(out)),
+                    "cafe_b200_branch_probabilities")
         return out
 
     def build_matrices(self, lambdas):

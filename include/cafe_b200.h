@@ -141,6 +141,17 @@ int  cafe_b200_eval_device(cafe_b200_ctx* ctx, const double* lambdas, int n_lamb
 int  cafe_b200_reconstruct(cafe_b200_ctx* ctx, const double* lambdas, int n_lambdas, int n_categories,
                            const double* prior_by_size, int32_t* states);
 
+/* Branch probabilities of the reconstructed size changes = compute_viterbi_sum for every (family, node)
+ * (src/gene_family_reconstructor.cpp:361-400; caller src/execute.cpp:165-176), from the device-resident matrices.
+ *   lambdas    HOST [n_lambdas] RAW (one set, no categories: the caller passes p_model->get_lambda())
+ *   node_sizes HOST [n_families][n_nodes] int32: reconstruction::reconstructed_size(family, node) for every node in tree
+ *              order (leaves: the observed count)
+ *   selected   HOST [n_families] flags or NULL (= all): the reference only asks for families with pvalue < threshold
+ *   out        HOST [n_families][n_nodes]: the probability, or -1 where the reference has no value
+ *              (root, size equal to the parent's, family not selected) */
+int  cafe_b200_branch_probabilities(cafe_b200_ctx* ctx, const double* lambdas, int n_lambdas, const int32_t* node_sizes,
+                                    const uint8_t* selected, double* out);
+
 /* ---- family p-values (compute_pvalues, src/probability.cpp:411-444) ------------------------- */
 
 /* The statistic both halves of compute_pvalues use: lk_i = max_j of the root partial-likelihood vector of family i

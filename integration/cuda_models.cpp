@@ -209,6 +209,19 @@ std::vector<double> cuda_bridge::root_max(const std::vector<double>& lambdas)
     return out;
 }
 
+std::vector<double> cuda_bridge::branch_probabilities(const std::vector<double>& lambdas, const std::vector<int>& node_sizes,
+                                                      const std::vector<unsigned char>& selected)
+{
+    // the context must hold exactly one row per family here (bind_rows de-duplicates count rows, but two families with
+    // the same counts still share their reconstruction, so the result is expanded by the caller through unique_of)
+    std::vector<double> out(_n_unique * _order.size(), -1.0);
+    static_assert(sizeof(int) == sizeof(int32_t), "int is 32 bits");
+    check(cafe_b200_branch_probabilities(_ctx, lambdas.data(), (int)_order.size(), reinterpret_cast<const int32_t*>(node_sizes.data()),
+                                         selected.empty() ? nullptr : selected.data(), out.data()),
+          "cafe_b200_branch_probabilities");
+    return out;
+}
+
 void cuda_bridge::reconstruct(const std::vector<double>& lambdas, int n_categories, const std::vector<double>& prior_by_size, std::vector<int>& states)
 {
     states.assign(_n_unique * n_categories * _internal.size(), 0);
@@ -477,6 +490,37 @@ std::vector<double> compute_pvalues_cuda(const clade* p_tree, const std::vector<
     if (const char* e = getenv("CAFE_B200_DEVICE")) device = atoi(e);
     int rc = cafe_b200_pvalues(device, cond.data(), mxr, nsim, observed.data(), (int64_t)observed.size(), result.data());
     if (rc != CAFE_B200_OK) throw std::runtime_error(std::string("cafe_b200_pvalues failed (") + std::to_string(rc) + "): " + cafe_b200_last_error(nullptr));
+    return result;
+}
+
+branch_probabilities compute_branch_probabilities_cuda(const clade* p_tree, const std::vector<gene_family>& families, const reconstruction* rec,
+                                                       const std::vector<double>& pvalues, double test_pvalue, const lambda* p_lambda,
+                                                       int max_family_size, int max_root_family_size)
+{
+    cuda_bridge bridge(p_tree, max_family_size, max_root_family_size);
+    bridge.bind(families);
+    const std::vector<const clade*>& order = bridge.nodes();
+    const size_t nn = order.size(), nu = bridge.unique_count();
+    // one row of reconstructed sizes per UNIQUE count row (identical families have identical reconstructions)
+    std::vector<int> sizes(nu * nn, 0);
+    std::vector<unsigned char> selected(nu, 0);
+    for (size_t i = 0; i < families.size(); ++i) {
+        const size_t u = bridge.unique_of(i);
+        if (!(pvalues[i] < test_pvalue)) continue;                   // src/execute.cpp:169
+        if (selected[u]) continue;
+        selected[u] = 1;
+        for (size_t v = 0; v < nn; ++v) sizes[u * nn + v] = rec->reconstructed_size(families[i], order[v]);
+    }
+    const std::vector<double> probs = bridge.branch_probabilities(bridge.lambda_table(p_lambda, std::vector<double>{1.0}), sizes, selected);
+    branch_probabilities result;
+    for (size_t i = 0; i < families.size(); ++i) {
+        if (!(pvalues[i] < test_pvalue)) continue;
+        const size_t u = bridge.unique_of(i);
+        for (size_t v = 0; v < nn; ++v) {
+            const double p = probs[u * nn + v];
+            result.set(families[i], order[v], p < 0 ? branch_probabilities::invalid() : branch_probabilities::branch_probability(p));
+        }
+    }
     return result;
 }
 

@@ -70,6 +70,9 @@ public:
     //! likelihood compute_pvalues uses (src/probability.cpp:308, 399).
     std::vector<double> root_max(const std::vector<double>& lambdas);
 
+    //! compute_viterbi_sum for every (bound row, node); node_sizes [rows][nodes in node order], selected [rows] or empty.
+    std::vector<double> branch_probabilities(const std::vector<double>& lambdas, const std::vector<int>& node_sizes, const std::vector<unsigned char>& selected);
+
     //! Pupko reconstruction on the device: states[unique family][category][internal node].
     void reconstruct(const std::vector<double>& lambdas, int n_categories, const std::vector<double>& prior_by_size, std::vector<int>& states);
 
@@ -78,6 +81,7 @@ public:
     int node_count() const { return (int)_order.size(); }
     const std::vector<const clade*>& internal_nodes() const { return _internal; }
     const std::vector<const clade*>& leaf_nodes() const { return _leaves; }       // = count-matrix columns
+    const std::vector<const clade*>& nodes() const { return _order; }             // apply_reverse_level_order, root last
     int max_family_size() const { return _mf; }
     int max_root_family_size() const { return _mrf; }
 
@@ -142,6 +146,13 @@ private:
 class matrix_cache;
 std::vector<double> compute_pvalues_cuda(const clade* p_tree, const std::vector<gene_family>& families, const lambda* p_lambda,
                                          const matrix_cache& cache, int number_of_simulations, int max_family_size, int max_root_family_size);
+
+//! Drop-in for the loop around compute_viterbi_sum (src/execute.cpp:165-176): branch probabilities of every family
+//! whose p-value is below `test_pvalue`, for every node, from the device-resident transition matrices
+//! (cafe_b200_branch_probabilities) instead of a host matrix_cache.
+branch_probabilities compute_branch_probabilities_cuda(const clade* p_tree, const std::vector<gene_family>& families, const reconstruction* rec,
+                                                       const std::vector<double>& pvalues, double test_pvalue, const lambda* p_lambda,
+                                                       int max_family_size, int max_root_family_size);
 
 //! Same decisions as build_models (src/core.cpp:16-50), instantiating the CUDA-backed subclasses.
 std::vector<model*> build_cuda_models(const input_parameters& user_input, user_data& user_data);

@@ -85,6 +85,7 @@ def lib():
         L.orc_pvalue.restype = C.c_double
         L.orc_pvalue.argtypes = [C.c_double, _dp, C.c_int]
         L.orc_pvalues.argtypes = [_dp, C.c_int, C.c_int, _dp, C.c_int64, _dp]
+        L.orc_branch_probabilities.argtypes = [C.POINTER(_Tree), _i32p, C.POINTER(C.c_uint8), C.c_int64, _dp, C.c_int, C.c_int, C.c_int, _dp]
         L.orc_init()
         _lib = L
     return _lib
@@ -226,6 +227,18 @@ def pvalues(cond, observed):
     obs = np.ascontiguousarray(observed, np.float64)
     out = np.zeros(len(obs))
     lib().orc_pvalues(_d(cond), cond.shape[0], cond.shape[1], _d(obs), len(obs), _d(out))
+    return out
+
+
+def branch_probabilities(flat, node_sizes, lambdas, mf, mrf, selected=None):
+    """compute_viterbi_sum per (family, node), src/gene_family_reconstructor.cpp:361-400; -1 = no value."""
+    th = TreeHandle(flat)
+    sizes = np.ascontiguousarray(node_sizes, np.int32)
+    lam = np.ascontiguousarray(lambdas, np.float64).ravel()
+    sel = None if selected is None else np.ascontiguousarray(selected, np.uint8)
+    out = np.zeros(sizes.shape)
+    lib().orc_branch_probabilities(th.ref(), sizes.ctypes.data_as(_i32p), None if sel is None else sel.ctypes.data_as(C.POINTER(C.c_uint8)),
+                                   sizes.shape[0], _d(lam), lam.size, mf, mrf, _d(out))
     return out
 
 

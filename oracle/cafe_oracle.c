@@ -633,3 +633,38 @@ void orc_pvalues(double* cond, int n_root_sizes, int n_sim, const double* observ
     }
 }
 
+/* src/gene_family_reconstructor.cpp:361-400 for every (family, node); -1 where the reference returns invalid(). */
+void orc_branch_probabilities(const orc_tree* tree, const int32_t* node_sizes, const uint8_t* selected, int64_t n_families,
+                              const double* lambdas, int n_lambdas, int max_family_size, int max_root_family_size, double* out)
+{
+    orc_init();
+    int mf = max_family_size, mrf = max_root_family_size;
+    int n = (mrf > mf ? mrf : mf) + 1;
+    int nn = tree->n_nodes;
+    matset ms;
+    matset_build(&ms, tree, lambdas, n);
+    (void)n_lambdas;
+    for (int64_t f = 0; f < n_families; ++f) {
+        for (int v = 0; v < nn; ++v) {
+            double result = -1.0;
+            int par = tree->parent[v];
+            if (par >= 0 && (!selected || selected[f])) {
+                int ps = node_sizes[f * nn + par], cs = node_sizes[f * nn + v];
+                if (ps != cs) {
+                    const double* m = ms.of_node[v];
+                    double pstar = m[(size_t)ps * n + cs];
+                    double acc = 0;
+                    for (int c = 0; c < mf; ++c) {
+                        double pm = m[(size_t)ps * n + c];
+                        if (pm == pstar) acc += pm / 2.0;
+                        else if (pm < pstar) acc += pm;
+                    }
+                    result = acc;
+                }
+            }
+            out[f * nn + v] = result;
+        }
+    }
+    matset_free(&ms);
+}
+

@@ -100,6 +100,11 @@ double orc_pvalue(double v, const double* sorted, int n);
 /* src/probability.cpp:310 + :391-409; cond [n_root_sizes][n_sim] is sorted in place */
 void   orc_pvalues(double* cond, int n_root_sizes, int n_sim, const double* observed, int64_t n_families, double* pvalues);
 
+/* src/gene_family_reconstructor.cpp:361-400 for every (family, node): node_sizes [F][n_nodes] reconstructed sizes in tree
+ * order, selected [F] or NULL, out [F][n_nodes] with -1 where the reference has no value. */
+void   orc_branch_probabilities(const orc_tree* tree, const int32_t* node_sizes, const uint8_t* selected, int64_t n_families,
+                                const double* lambdas, int n_lambdas, int max_family_size, int max_root_family_size, double* out);
+
 #ifdef __cplusplus
 }
 #endif

@@ -415,6 +415,31 @@ int cmd_eval(const args_t& a)
                 dr.ints(row.data(), row.size());
             }
         }
+        if (a.has("viterbi")) {
+            // compute_viterbi_sum for every family and node (src/execute.cpp:165-176 with every family selected):
+            // dump = ints [F][nodes] reconstructed sizes (node_order), then doubles [F][nodes] probabilities (-1 = invalid)
+            const int mf = s.data.max_family_size;
+            std::vector<double> pv(F, 0.0);
+            branch_probabilities probs;
+#ifdef WITH_CUDA_MODELS
+            if (a.integer("cuda", 0))
+                probs = compute_branch_probabilities_cuda(s.data.p_tree, s.data.gene_families, rec.get(), pv, 1.0, m->get_lambda(), mf, s.data.max_root_family_size);
+            else
+#endif
+            for (auto& fam : s.data.gene_families)
+                for (auto c : s.order) probs.set(fam, c, compute_viterbi_sum(c, fam, rec.get(), mf, calc, m->get_lambda()));
+            dumper dv(a.str("dumpviterbi"));
+            std::vector<int> sz;
+            std::vector<double> val;
+            for (auto& fam : s.data.gene_families)
+                for (auto c : s.order) {
+                    sz.push_back(rec->reconstructed_size(fam, c));
+                    auto bp = probs.at(fam, c);
+                    val.push_back(bp._is_valid ? bp._value : -1.0);
+                }
+            dv.ints(sz.data(), sz.size());
+            dv.doubles(val.data(), val.size());
+        }
     }
     printf("}\n");
     return 0;

@@ -247,6 +247,24 @@ def pvalues(tmp):
     print("pvalues", F, "families,", mrf * nsim, "simulated;", np.unique(pv).size, "distinct p-values", flush=True)
 
 
+def viterbi(tmp):
+    """compute_viterbi_sum (src/gene_family_reconstructor.cpp:361-400) for every node of the first 400 root-filtered mammal
+    families after a base-model reconstruction at lambda = 0.002: reconstructed sizes of all nodes and the probabilities."""
+    E = {"tree": os.path.join(EX, "mammals_tree.txt"), "fam": os.path.join(EX, "mammal_gene_families.txt")}
+    limit, lam = 400, 0.002
+    dump = os.path.join(tmp, "vit.bin")
+    r = orc.run_ref("eval", limit=limit, recon=True, viterbi=True, dumprecon=os.path.join(tmp, "vit.rec"), dumpviterbi=dump, **E, **{"lambda": lam})
+    F, nn = r["n_families"], len(r["node_order"])
+    raw = open(dump, "rb").read()
+    sizes = np.frombuffer(raw, np.int32, F * nn, 0).reshape(F, nn)
+    probs = np.frombuffer(raw, np.float64, F * nn, sizes.nbytes).reshape(F, nn)
+    assert sizes.nbytes + probs.nbytes == len(raw) and sizes.max() < 32768
+    meta = {"limit": limit, "lambda": lam, "max_family_size": r["max_family_size"], "max_root_family_size": r["max_root_family_size"],
+            "node_order": r["node_order"]}
+    np.savez_compressed(os.path.join(GOLD, "mammal_viterbi.npz"), meta=json.dumps(meta), node_sizes=sizes.astype(np.int16), probabilities=probs)
+    print("viterbi", F, "families,", int((probs >= 0).sum()), "valid branch probabilities", flush=True)
+
+
 def fits():
     E = {"tree": os.path.join(EX, "mammals_tree.txt"), "fam": os.path.join(EX, "mammal_gene_families.txt")}
     path = os.path.join(GOLD, "fits.json")
@@ -277,7 +295,7 @@ def main():
         raise SystemExit("oracle/_ref/ref_harness missing: run `make -C oracle ref` (needs /root/reference)")
     os.makedirs(GOLD, exist_ok=True)
     with tempfile.TemporaryDirectory() as tmp:
-        steps = args.only.split(",") if args.only else ["inputs", "scalars", "matrices", "unit", "mammal", "pvalues"]
+        steps = args.only.split(",") if args.only else ["inputs", "scalars", "matrices", "unit", "mammal", "pvalues", "viterbi"]
         flat = ids = counts = None
         if "inputs" in steps or "mammal" in steps:
             flat, ids, counts = mammal_inputs()
@@ -291,6 +309,8 @@ def main():
             mammal_outputs(tmp, flat, ids, counts)
         if "pvalues" in steps:
             pvalues(tmp)
+        if "viterbi" in steps:
+            viterbi(tmp)
         if args.fits:
             fits()
 
