@@ -182,7 +182,7 @@ def run_reference_arm(args):
             "config": workload_config(args, 1), "cpu_baseline": {k: base[k] for k in ("value", "unit", "cores", "kind", "sample")},
             "e2e": {"value": value, "unit": "families/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
     line["cpu_baseline"]["value"] = value
-    print(json.dumps(line), flush=True)
+    emit(line)
 
 
 def workload_config(args, world):
@@ -217,7 +217,27 @@ def measured_traffic(families_per_launch):
         return None, None
 
 
+_REAL_STDOUT = None
+
+
+def claim_stdout():
+    """The contract is ONE JSON line on stdout.  Libraries print there too (NCCL's version banner, torchrun notices), so
+    file descriptor 1 is pointed at stderr for the whole run and the result line goes to a private copy of the original."""
+    global _REAL_STDOUT
+    if _REAL_STDOUT is None:
+        sys.stdout.flush()
+        _REAL_STDOUT = os.fdopen(os.dup(1), "w")
+        os.dup2(2, 1)
+
+
+def emit(line: dict):
+    out = _REAL_STDOUT or sys.stdout
+    out.write(json.dumps(line) + "\n")
+    out.flush()
+
+
 def main():
+    claim_stdout()
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
     ap.add_argument("--steps", type=int, default=5)
@@ -242,7 +262,6 @@ def main():
     if world > 1:
         import torch.distributed as dist
         os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
-        os.environ.setdefault("NCCL_DEBUG_FILE", "/dev/stderr")      # NCCL's version banner must not precede the JSON line on stdout
         dist.init_process_group("nccl", device_id=torch.device("cuda", local))
     if engine.device_count() < 1:
         raise SystemExit("bench.py needs a CUDA device: cafexp_b200 has no CPU fallback")
@@ -363,7 +382,7 @@ def main():
         if world == 1 and not args.no_cpu_baseline:
             cb = cpu_reference_rate(tree, newick, counts, n_full=F)
             line["cpu_baseline"] = {k: cb[k] for k in ("value", "unit", "cores", "kind", "sample")}
-        print(json.dumps(line), flush=True)
+        emit(line)
     eng.close()
     if world > 1:
         dist.barrier()
