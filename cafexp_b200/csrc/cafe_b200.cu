@@ -730,22 +730,25 @@ int cafe_b200_create(cafe_b200_ctx** out, const cafe_b200_tree* tree, const int3
     for (auto& e : c->ev) CREATE_TRY(cudaEventCreate(&e));
 
     // Shared-memory budget: a deep matrix ring matters more than a fourth vector slot (the bulk copies need
-    // ~bandwidth x L2 latency bytes in flight; a spilled vector costs two 40 KB L2 round trips per tile),
-    // so take the deepest ring that still leaves three slots (two as a last resort).
+    // ~bandwidth x L2 latency bytes in flight; a spilled vector costs two L2 round trips per tile), so take the
+    // deepest ring that still leaves three slots, two as a last resort.  Each consumer group gets half the ring and
+    // needs at least two stages of its own: it loads the next stage's fragments before it releases the current one.
     int slots = 0;
-    for (int stages : {8, 4, 2}) {
-        int sl = 0;
+    auto slots_with = [&](int stages) {
         switch (c->mb) {
-        case 1: sl = PruneSmem<1>::max_slots(c->smem_optin, stages); break;
-        case 2: sl = PruneSmem<2>::max_slots(c->smem_optin, stages); break;
-        case 3: sl = PruneSmem<3>::max_slots(c->smem_optin, stages); break;
-        case 4: sl = PruneSmem<4>::max_slots(c->smem_optin, stages); break;
-        case 5: sl = PruneSmem<5>::max_slots(c->smem_optin, stages); break;
-        case 6: sl = PruneSmem<6>::max_slots(c->smem_optin, stages); break;
-        case 7: sl = PruneSmem<7>::max_slots(c->smem_optin, stages); break;
-        default: sl = PruneSmem<8>::max_slots(c->smem_optin, stages); break;
+        case 1: return PruneSmem<1>::max_slots(c->smem_optin, stages);
+        case 2: return PruneSmem<2>::max_slots(c->smem_optin, stages);
+        case 3: return PruneSmem<3>::max_slots(c->smem_optin, stages);
+        case 4: return PruneSmem<4>::max_slots(c->smem_optin, stages);
+        case 5: return PruneSmem<5>::max_slots(c->smem_optin, stages);
+        case 6: return PruneSmem<6>::max_slots(c->smem_optin, stages);
+        case 7: return PruneSmem<7>::max_slots(c->smem_optin, stages);
+        default: return PruneSmem<8>::max_slots(c->smem_optin, stages);
         }
-        if (sl >= 3 || (stages == 2 && sl >= 2)) { slots = sl; c->n_stages = stages; break; }
+    };
+    for (int stages : {8, 4}) {
+        const int sl = slots_with(stages);
+        if (sl >= 3 || (stages == 2 * GROUPS && sl >= 2)) { slots = sl; c->n_stages = stages; break; }
     }
     if (slots < 2) { g_create_error = "not enough shared memory for two vector slots"; cafe_b200_destroy(c); return CAFE_B200_ERR_LIMIT; }
     c->n_slots = c->hw_slots = slots;

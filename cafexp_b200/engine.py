@@ -19,6 +19,7 @@ LIB_PATH = os.path.join(HERE, "libcafe_b200.so")
 BASE_LOGMAX = 0
 GAMMA_LINSUM = 1
 OPT_RESCALE = 1
+OPT_MAX_SLOTS = 2
 
 ERR_NAMES = {-1: "ERR_ARG", -2: "ERR_CUDA", -3: "ERR_COUNT_RANGE", -4: "ERR_LIMIT"}
 
@@ -187,6 +188,10 @@ class Engine:
 
     def set_rescale(self, on: bool):
         self._check(self._lib.cafe_b200_set_option(self._h, OPT_RESCALE, 1 if on else 0), "set_option")
+
+    def set_max_slots(self, n: int):
+        """Cap the shared-memory vector slots (>= 2): fewer slots force the schedule to spill (tests)."""
+        self._check(self._lib.cafe_b200_set_option(self._h, OPT_MAX_SLOTS, int(n)), "set_option")
 
     def set_stream(self, cuda_stream_ptr: int):
         self._check(self._lib.cafe_b200_set_stream(self._h, C.c_void_p(cuda_stream_ptr)), "set_stream")
