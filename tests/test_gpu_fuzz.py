@@ -3,6 +3,8 @@ balanced and caterpillar), matrix sizes across every row-block count (N = 6 .. 2
 lambdas, error models with 3 and 5 deviations, shared-memory slot limits that force spills, ragged family counts,
 power-of-two rescaling.  Every case checks evaluation, root vectors, the p-value statistic and the Pupko
 reconstruction.  Needs a B200."""
+import os
+
 import numpy as np
 import pytest
 
@@ -72,7 +74,7 @@ def make_case(seed):
                 slots=int(rng.choice([0, 0, 2, 3])), rescale=bool(rng.random() < 0.3), n_leaves=n_leaves, shape=shape)
 
 
-@pytest.mark.parametrize("seed", range(40))
+@pytest.mark.parametrize("seed", range(int(os.environ.get("CAFE_B200_FUZZ_SEEDS", "40"))))
 def test_random_case_against_oracle(seed):
     c = make_case(seed)
     flat, mf, mrf, counts, k, lams = c["flat"], c["mf"], c["mrf"], c["counts"], c["k"], c["lams"]
