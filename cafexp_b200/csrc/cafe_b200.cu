@@ -261,10 +261,12 @@ struct cafe_b200_ctx {
     int64_t n_families = 0;
     int64_t n_tiles = 0;
     int max_count = 0;
-    Schedule sched;                     // unfused ops: reconstruction kernel, pruning with an error model
-    std::vector<FusedOp> fused;         // fused ops: pruning without error model
-    int n_slots = 0;
-    int hw_slots = 0;
+    Schedule sched;                     // reconstruction kernel: op list for n_slots slots
+    Schedule psched;                    // pruning kernel: op list for prune_slots slots (unfused form: used with an error model)
+    std::vector<FusedOp> fused;         // psched with leaf siblings fused: pruning without error model
+    int n_slots = 0, hw_slots = 0;              // reconstruction kernel (32-family tiles)
+    int prune_slots = 0, prune_hw_slots = 0;    // pruning kernel (n_groups x 16-family tiles)
+    int n_groups = 2;                   // consumer groups of the pruning kernel (3 when shared memory allows)
     int n_stages = 4;                   // pruning ring depth
     int rescale = 0;
     int cap_k = 0;                      // categories the k-dependent buffers are sized for
@@ -296,8 +298,9 @@ struct cafe_b200_ctx {
     uint8_t* d_family_fail = nullptr;
     double* d_partial = nullptr;
     double* d_result = nullptr;
-    double* d_scratch = nullptr;
-    int* d_scratch_exp = nullptr;
+    double* d_scratch = nullptr;        // reconstruction spill area
+    double* d_pscratch = nullptr;       // pruning spill area [SMs][n_spill][tile families x LDV]
+    int* d_pscratch_exp = nullptr;
     // pinned staging
     unsigned char* h_stage = nullptr;
     size_t h_stage_bytes = 0;
@@ -343,7 +346,7 @@ int ensure_category_buffers(cafe_b200_ctx* c, int k)
     CUDA_TRY(c, dev_alloc(&c->d_cat_lk, (size_t)c->n_families * k));
     CUDA_TRY(c, dev_alloc(&c->d_fail, (size_t)c->n_families * k, true));
     CUDA_TRY(c, dev_alloc(&c->d_catprobs, (size_t)k));
-    c->pops_cap = (int)c->sched.ops.size();
+    c->pops_cap = (int)c->psched.ops.size();
     CUDA_TRY(c, dev_alloc(&c->d_pops, (size_t)k * c->pops_cap));
     // staging: keys + powc + mat_of + prior + logprior + catprobs + per-category ops
     size_t need = keys * sizeof(KeyParams) + keys * c->n * sizeof(double) + keys * sizeof(int) + (2 * (size_t)c->n + k + 64) * sizeof(double)
@@ -411,8 +414,8 @@ int stage_and_build(cafe_b200_ctx* c, const double* lambdas, int n_lambdas, int 
     for (int cat = 0; cat < k; ++cat) h_cat[cat] = cat_probs ? cat_probs[cat] : 1.0;
     // per-category pruning ops with matrix slots and count columns resolved
     POp* h_pops = reinterpret_cast<POp*>((reinterpret_cast<uintptr_t>(h_mat_of + slots) + 15) & ~uintptr_t(15));   // POp is 16-byte aligned
-    if ((int)c->sched.ops.size() > c->pops_cap) return fail(c, CAFE_B200_ERR_ARG, "schedule grew after the category buffers were sized");
-    const std::vector<FusedOp> plain = c->d_err ? fuse_schedule(c->sched.ops, false) : std::vector<FusedOp>();
+    if ((int)c->psched.ops.size() > c->pops_cap) return fail(c, CAFE_B200_ERR_ARG, "schedule grew after the category buffers were sized");
+    const std::vector<FusedOp> plain = c->d_err ? fuse_schedule(c->psched.ops, false) : std::vector<FusedOp>();
     const std::vector<FusedOp>& fo = c->d_err ? plain : c->fused;
     c->n_pops = (int)fo.size();
     for (int cat = 0; cat < k; ++cat)
@@ -456,39 +459,46 @@ int stage_and_build(cafe_b200_ctx* c, const double* lambdas, int n_lambdas, int 
     return CAFE_B200_OK;
 }
 
-template <int MB>
-int launch_prune_mb(cafe_b200_ctx* c, const PruneParams& p)
+template <int MB, int NG>
+int launch_prune_mbg(cafe_b200_ctx* c, const PruneParams& p)
 {
-    using L = PruneSmem<MB>;
-    PruneParams q = p;
-    const int ops_bytes = GROUPS * q.n_ops * (int)sizeof(POp);
-    q.ops_in_smem = (L::total_bytes(c->n_slots, c->n_stages, ops_bytes) <= c->smem_optin) ? 1 : 0;
-    const int smem = L::total_bytes(c->n_slots, c->n_stages, q.ops_in_smem ? ops_bytes : 0);
-    CUDA_TRY(c, cudaFuncSetAttribute(prune_kernel<MB>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
-    const int64_t items = q.n_tiles * q.n_categories;        // one item = one group's 16-family tile of one category
-    const int grid = (int)std::min<int64_t>((items + GROUPS - 1) / GROUPS, c->sm_count);
-    prune_kernel<MB><<<grid, PRUNE2_THREADS, smem, c->stream>>>(q);
+    using L = PruneSmem<MB, NG>;
+    const int smem = L::total_bytes(c->prune_slots, c->n_stages);
+    CUDA_TRY(c, cudaFuncSetAttribute(prune_kernel<MB, NG>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
+    const int64_t items = p.n_tiles * p.n_categories;        // one item = one tile of NG x 16 families of one category
+    const int grid = (int)std::min<int64_t>(items, c->sm_count);
+    prune_kernel<MB, NG><<<grid, prune_threads(NG), smem, c->stream>>>(p);
     CUDA_TRY(c, cudaGetLastError());
     c->launches++;
     return CAFE_B200_OK;
 }
 
+template <int MB>
+int launch_prune_mb(cafe_b200_ctx* c, const PruneParams& p)
+{
+    return c->n_groups == 3 ? launch_prune_mbg<MB, 3>(c, p) : launch_prune_mbg<MB, 2>(c, p);
+}
+
 int launch_prune(cafe_b200_ctx* c, int k, int mode, double* root_out)
 {
     if (c->n_families == 0) return CAFE_B200_OK;
+    const int pft = c->n_groups * GFT;
     PruneParams p;
     memset(&p, 0, sizeof(p));
     p.n_families = c->n_families; p.n_leaves = c->n_leaves; p.n_nodes = c->tree.n_nodes; p.n_categories = k;
     p.mf = c->mf; p.mrf = c->mrf; p.n_ops = c->n_pops; p.n_kchunks = c->n_kchunks; p.mode = mode;
-    p.rescale = c->rescale; p.n_spill = std::max(1, c->sched.n_spill); p.err_rows = c->err_rows; p.err_ndev = c->err_ndev;
-    p.counts_in_smem = (FT * c->n_leaves * 2 <= CNT_CAP_BYTES) ? 1 : 0;
-    p.n_slots = c->n_slots; p.n_tiles = (c->n_families + GFT - 1) / GFT;
-    // the ring is split between the two consumer groups: c->n_stages in {8,4,2} -> {4,2,1} stages each
-    p.n_stages = c->n_stages / GROUPS; p.stage_shift = p.n_stages == 4 ? 2 : (p.n_stages == 2 ? 1 : 0);
+    p.rescale = c->rescale; p.n_spill = std::max(1, c->psched.n_spill); p.err_rows = c->err_rows; p.err_ndev = c->err_ndev;
+    p.counts_in_smem = (pft * c->n_leaves * 2 <= PRUNE_CNT_CAP_BYTES) ? 1 : 0;
+    p.n_slots = c->prune_slots; p.n_tiles = (c->n_families + pft - 1) / pft;
+    p.n_stages = c->n_stages; p.stage_shift = c->n_stages == 8 ? 3 : (c->n_stages == 4 ? 2 : 1);
+    // consecutive groups start a few ring stages apart: half the ring depth in chunk times, a chunk being
+    // 2*PPS*MB DMMAs of 16 cycles for each of the n_groups warps on a sub-partition
+    p.stagger_cycles = (c->n_stages / 2) * (2 * PPS * c->mb * 16 * c->n_groups) / (c->n_groups - 1);
+    if (const char* e = getenv("CAFE_B200_STAGGER")) p.stagger_cycles = atoi(e);
     p.ops = c->d_pops; p.counts = c->d_counts;
     p.mp = c->d_mp; p.mt = c->d_mt; p.mp_stride = c->mp_stride; p.mt_stride = c->mt_stride;
     p.err = c->d_err; p.prior = c->d_prior; p.logprior = c->d_logprior; p.cat_probs = c->d_catprobs;
-    p.scratch = c->d_scratch; p.scratch_exp = c->d_scratch_exp;
+    p.scratch = c->d_pscratch; p.scratch_exp = c->d_pscratch_exp;
     p.cat_lk = c->d_cat_lk; p.fail = c->d_fail; p.root_out = root_out;
     switch (c->mb) {
     case 1: return launch_prune_mb<1>(c, p);
@@ -566,20 +576,63 @@ int launch_pupko(cafe_b200_ctx* c, int k, int32_t* states_host)
     return rc;
 }
 
-// (Re)build the op list for c->n_slots slots and size the spill scratch for it.
+// Shared-memory budget of the two tree-walking kernels.  Pruning: two consumer groups (32-family tiles) with three
+// vector slots and the deepest ring that fits (8 stages, else 4), two slots as a last resort.  A three-group layout
+// (48-family tiles, two slots; CAFE_B200_GROUPS=3) exists for experiments: the third MMA warp per sub-partition helps
+// an isolated K loop (scripts/kloop_mix.cu: 0.81 vs 0.76 of the DMMA rate) but in the full kernel the 128-register
+// cap of 448 threads and the extra spills of a two-slot schedule cost more (measured 0.685 vs 0.706).
+template <int MB>
+bool plan_shared_memory_mb(cafe_b200_ctx* c)
+{
+    const int lim = c->smem_optin;
+    c->hw_slots = std::min(MAX_SLOTS, (lim - PupkoSmem<MB>::total_bytes(0)) / PupkoSmem<MB>::SLOT_BYTES);
+    c->prune_hw_slots = 0;
+    const char* e = getenv("CAFE_B200_GROUPS");
+    if (e && atoi(e) == 3)
+        for (int stages : {8, 4}) {
+            const int sl = PruneSmem<MB, 3>::max_slots(lim, stages);
+            if (sl >= 2) { c->n_groups = 3; c->n_stages = stages; c->prune_hw_slots = sl; break; }
+        }
+    if (!c->prune_hw_slots)
+        for (int stages : {8, 4}) {
+            const int sl = PruneSmem<MB, 2>::max_slots(lim, stages);
+            if (sl >= 3 || (stages == 4 && sl >= 2)) { c->n_groups = 2; c->n_stages = stages; c->prune_hw_slots = sl; break; }
+        }
+    c->n_slots = c->hw_slots;
+    c->prune_slots = c->prune_hw_slots;
+    return c->hw_slots >= 2 && c->prune_hw_slots >= 2;
+}
+
+bool plan_shared_memory(cafe_b200_ctx* c)
+{
+    switch (c->mb) {
+    case 1: return plan_shared_memory_mb<1>(c);
+    case 2: return plan_shared_memory_mb<2>(c);
+    case 3: return plan_shared_memory_mb<3>(c);
+    case 4: return plan_shared_memory_mb<4>(c);
+    case 5: return plan_shared_memory_mb<5>(c);
+    case 6: return plan_shared_memory_mb<6>(c);
+    case 7: return plan_shared_memory_mb<7>(c);
+    default: return plan_shared_memory_mb<8>(c);
+    }
+}
+
+// (Re)build the op lists (reconstruction: n_slots, pruning: prune_slots) and size the spill scratch for them.
 int upload_schedule(cafe_b200_ctx* c)
 {
     c->sched = ScheduleBuilder(c->tree, c->n_slots).build();
-    c->fused = fuse_schedule(c->sched.ops, true);
-    if ((int)c->sched.ops.size() > c->pops_cap) c->cap_k = 0;       // force the per-category op buffers to be re-sized
-    cudaFree(c->d_ops); cudaFree(c->d_scratch); cudaFree(c->d_scratch_exp);
-    c->d_ops = nullptr; c->d_scratch = nullptr; c->d_scratch_exp = nullptr;
+    c->psched = ScheduleBuilder(c->tree, c->prune_slots).build();
+    c->fused = fuse_schedule(c->psched.ops, true);
+    if ((int)c->psched.ops.size() > c->pops_cap) c->cap_k = 0;       // force the per-category op buffers to be re-sized
+    cudaFree(c->d_ops); cudaFree(c->d_scratch); cudaFree(c->d_pscratch); cudaFree(c->d_pscratch_exp);
+    c->d_ops = nullptr; c->d_scratch = nullptr; c->d_pscratch = nullptr; c->d_pscratch_exp = nullptr;
     CUDA_TRY(c, dev_alloc(&c->d_ops, c->sched.ops.size()));
     CUDA_TRY(c, cudaMemcpy(c->d_ops, c->sched.ops.data(), c->sched.ops.size() * sizeof(Op), cudaMemcpyHostToDevice));
-    const size_t slot_doubles = (size_t)FT * ldv_of(c->mb);
-    const size_t nsp = (size_t)std::max(1, c->sched.n_spill);
-    CUDA_TRY(c, dev_alloc(&c->d_scratch, (size_t)c->sm_count * nsp * slot_doubles, true));
-    CUDA_TRY(c, dev_alloc(&c->d_scratch_exp, (size_t)c->sm_count * nsp * FT, true));
+    const size_t ldv = ldv_of(c->mb);
+    CUDA_TRY(c, dev_alloc(&c->d_scratch, (size_t)c->sm_count * std::max(1, c->sched.n_spill) * FT * ldv, true));
+    const size_t pft = (size_t)c->n_groups * GFT, pnsp = (size_t)std::max(1, c->psched.n_spill);
+    CUDA_TRY(c, dev_alloc(&c->d_pscratch, (size_t)c->sm_count * pnsp * pft * ldv, true));
+    CUDA_TRY(c, dev_alloc(&c->d_pscratch_exp, (size_t)c->sm_count * pnsp * pft, true));
     return CAFE_B200_OK;
 }
 
@@ -657,7 +710,7 @@ void cafe_b200_destroy(cafe_b200_ctx* c)
     cudaFree(c->d_lgamma); cudaFree(c->d_err); cudaFree(c->d_prior); cudaFree(c->d_logprior); cudaFree(c->d_catprobs);
     cudaFree(c->d_pops);
     cudaFree(c->d_cat_lk); cudaFree(c->d_fail); cudaFree(c->d_family_lnl); cudaFree(c->d_family_fail); cudaFree(c->d_partial);
-    cudaFree(c->d_result); cudaFree(c->d_scratch); cudaFree(c->d_scratch_exp);
+    cudaFree(c->d_result); cudaFree(c->d_scratch); cudaFree(c->d_pscratch); cudaFree(c->d_pscratch_exp);
     if (c->h_stage) cudaFreeHost(c->h_stage);
     if (c->h_result) cudaFreeHost(c->h_result);
     if (c->staged) cudaEventDestroy(c->staged);
@@ -729,29 +782,7 @@ int cafe_b200_create(cafe_b200_ctx** out, const cafe_b200_tree* tree, const int3
     CREATE_TRY(cudaEventRecord(c->staged, c->stream));
     for (auto& e : c->ev) CREATE_TRY(cudaEventCreate(&e));
 
-    // Shared-memory budget: a deep matrix ring matters more than a fourth vector slot (the bulk copies need
-    // ~bandwidth x L2 latency bytes in flight; a spilled vector costs two L2 round trips per tile), so take the
-    // deepest ring that still leaves three slots, two as a last resort.  Each consumer group gets half the ring and
-    // needs at least two stages of its own: it loads the next stage's fragments before it releases the current one.
-    int slots = 0;
-    auto slots_with = [&](int stages) {
-        switch (c->mb) {
-        case 1: return PruneSmem<1>::max_slots(c->smem_optin, stages);
-        case 2: return PruneSmem<2>::max_slots(c->smem_optin, stages);
-        case 3: return PruneSmem<3>::max_slots(c->smem_optin, stages);
-        case 4: return PruneSmem<4>::max_slots(c->smem_optin, stages);
-        case 5: return PruneSmem<5>::max_slots(c->smem_optin, stages);
-        case 6: return PruneSmem<6>::max_slots(c->smem_optin, stages);
-        case 7: return PruneSmem<7>::max_slots(c->smem_optin, stages);
-        default: return PruneSmem<8>::max_slots(c->smem_optin, stages);
-        }
-    };
-    for (int stages : {8, 4}) {
-        const int sl = slots_with(stages);
-        if (sl >= 3 || (stages == 2 * GROUPS && sl >= 2)) { slots = sl; c->n_stages = stages; break; }
-    }
-    if (slots < 2) { g_create_error = "not enough shared memory for two vector slots"; cafe_b200_destroy(c); return CAFE_B200_ERR_LIMIT; }
-    c->n_slots = c->hw_slots = slots;
+    if (!plan_shared_memory(c)) { g_create_error = "not enough shared memory for two vector slots"; cafe_b200_destroy(c); return CAFE_B200_ERR_LIMIT; }
     if (upload_schedule(c) != CAFE_B200_OK) { g_create_error = c->error; cafe_b200_destroy(c); return CAFE_B200_ERR_CUDA; }
 
     CREATE_TRY(dev_alloc(&c->d_counts, (size_t)n_families * n_leaves));
@@ -829,6 +860,7 @@ int cafe_b200_set_option(cafe_b200_ctx* c, int option, int value)
         CUDA_TRY(c, cudaSetDevice(c->device));
         CUDA_TRY(c, cudaStreamSynchronize(c->stream));
         c->n_slots = std::min(value, c->hw_slots);
+        c->prune_slots = std::min(value, c->prune_hw_slots);
         return upload_schedule(c);
     }
     return fail(c, CAFE_B200_ERR_ARG, "unknown option");

@@ -80,10 +80,10 @@ struct PruneParams {
     int err_ndev;
     int counts_in_smem;
     int n_slots;
-    int n_stages;           // ring depth of one consumer group (power of two)
+    int n_stages;           // ring depth (power of two)
     int stage_shift;        // log2(n_stages)
-    int ops_in_smem;        // per-group copies of the op list live in shared memory
-    int64_t n_tiles;        // tiles of FT/2 families (one per consumer group and work item)
+    int stagger_cycles;     // one-time start delay between consecutive consumer groups (SM cycles)
+    int64_t n_tiles;        // tiles of (groups x 16) families = work items per category
     // device pointers
     const POp* ops;                 // [k][n_ops]
     const int32_t* counts;          // [F][n_leaves]

@@ -10,60 +10,62 @@
 //   base_model root max of log L + log prior src/base_model.cpp:89-106
 //   gamma_model::prune                       src/gamma_core.cpp:144-166
 //
-// Design (B200): one persistent thread block per SM walks a host-built post-order schedule for a
-// tile of FT=32 families of one rate category.  Partial-likelihood vectors never leave the SM:
-// they sit in shared-memory slots V[family][size].  An internal edge is the dense FP64 contraction
-//      Y[NR x FT] = M_edge[NR x K] * V_child[K x FT]
-// issued as mma.sync.m8n8k4.f64 (DMMA), accumulators in registers for the whole K loop.  The matrix
-// streams from L2 through a shared-memory ring filled by 1-D bulk async copies (TMA engine,
-// cp.async.bulk + mbarrier complete_tx) issued by a dedicated producer warp that runs ahead across ops.
+// Design (B200): one persistent thread block per SM walks a host-built post-order schedule for a tile of
+// NG*16 families of one rate category.  Partial-likelihood vectors never leave the SM: they sit in shared-memory
+// slots V[family][size].  An internal edge is the dense FP64 contraction
+//      Y[NR x 16] = M_edge[NR x K] * V_child[K x 16]
+// issued as mma.sync.m8n8k4.f64 (DMMA), accumulators in registers for the whole K loop.  The matrix streams from
+// L2 through a shared-memory ring filled by 1-D bulk async copies (TMA engine, cp.async.bulk + mbarrier
+// complete_tx) issued by two producer warps (alternate chunks) that run ahead across ops and items.
 //
-// The 8 consumer warps form TWO INDEPENDENT GROUPS of 4 warps (one warp per SM sub-partition each).  A group
-// is a virtual thread block: it owns families [16g, 16g+16) of every slot, its own half of the matrix ring,
-// its own named barrier and its own stream of work items (16-family tiles), so nothing couples the two groups
-// except the FP64 tensor pipe they share.  While one group is between GEMMs (epilogue, child product, leaf
-// gathers, barriers, waiting for L2) the other has the pipe to itself and consumes chunks twice as fast.
-// Each group's ring is fed by PRODUCERS_PER_GROUP producer warps taking alternate chunks: one elected thread
-// needs ~300-400 cycles per chunk (try_wait on the empty barrier ~90, expect_tx, bulk-copy issue, address
-// arithmetic — measured), which is as long as a lone group needs to consume it, so a single producer per group
-// would pin the group to the shared-pipe rate and the decoupling would buy nothing (measured: 0.65 of peak
-// either way).  Inside a GEMM the A/B fragments are double-buffered in registers across ring stages, so a warp
-// running alone can still issue DMMAs back to back.
+// The consumer warps form NG = 2 GROUPS of 4 warps (one warp per SM sub-partition each).  Group g owns families
+// [16g, 16g+16) of the tile (its rows of every slot), has its own named barrier and walks the same op list at its
+// own pace; both groups consume the SAME matrix stream from the shared ring (a stage is released when every consumer
+// warp has read it), so the L2 traffic per flop is that of a 32-family tile and the groups can drift up to one ring
+// depth (8 chunks) apart: while one group is between GEMMs (epilogue, child product, leaf gathers at L2 latency,
+// barriers) the other keeps the FP64 pipe busy.  Inside a GEMM the A/B fragments are double-buffered in registers
+// across ring stages; the leaf-sibling factors of the epilogue are gathered after the K loop, when the fragment
+// registers are free.  NG = 3 (48-family tiles, two slots) is compiled for experiments, see plan_shared_memory.
 //
-// The epilogue multiplies the product straight into the parent's accumulator slot (child product);
-// leaf edges are gathers of one matrix column (or an error-model stencil of columns), not GEMMs.
-// HBM traffic per family is just its leaf counts in and k+1 doubles out.
+// What bounds the kernel (scripts/kloop_mix.cu rebuilds the loop from its parts on the same geometry): the bare
+// loop runs at the DMMA peak; the per-stage mbarrier wait / arrive costs 11 %, the FP64 multiplies of the epilogue
+// 4 %, a leaf gather at L2 latency per GEMM 11 % (the tree has one per three GEMMs), and op dispatch, count lookups,
+// spills and the root reduction the rest: 0.71 of the DMMA peak in all (profiles/r01_pruning_kernel_experiments.md).
+//
+// The epilogue multiplies the product straight into the parent's accumulator slot (child product), fused with a
+// leaf sibling's gathered column; leaf edges are gathers of one matrix column (or an error-model stencil of
+// columns), not GEMMs.  HBM traffic per family is just its leaf counts in and k+1 doubles out.
 #pragma once
 
 #include "common.cuh"
 
 namespace cafe {
 
-constexpr int GROUPS = 2;
-constexpr int GROUP_WARPS = CONSUMER_WARPS / GROUPS;     // 4: one per SM sub-partition
+constexpr int GROUP_WARPS = 4;                           // one per SM sub-partition
 constexpr int GROUP_THREADS = GROUP_WARPS * 32;
-constexpr int GFT = FT / GROUPS;                         // 16 families per group = 2 n8 blocks
+constexpr int GFT = 16;                                  // families per group = 2 n8 blocks
 constexpr int FPW = GFT / GROUP_WARPS;                   // 4 families per warp in the gather / root ops
-constexpr int PRODUCERS_PER_GROUP = 2;                   // producer warps per group, taking alternate chunks
-constexpr int PRUNE2_THREADS = CONSUMER_THREADS + GROUPS * PRODUCERS_PER_GROUP * 32;
+constexpr int PRODUCER_WARPS = 2;                        // take alternate chunks of the one matrix stream
+constexpr int MAX_GROUPS = 3;
+constexpr int PRUNE_CNT_CAP_BYTES = 12288;               // staged leaf counts (uint16) of a 48-family tile, if they fit
+__host__ __device__ constexpr int prune_threads(int ng) { return (ng * GROUP_WARPS + PRODUCER_WARPS) * 32; }
 
-template <int MB>
+template <int MB, int NG>
 struct PruneSmem {
+    static constexpr int PFT = NG * GFT;                 // families per thread-block tile
     static constexpr int NR = nr_of(MB);
     static constexpr int LDV = ldv_of(MB);
     static constexpr int STAGE_DOUBLES = stage_doubles(MB);
     static constexpr int STAGE_BYTES = STAGE_DOUBLES * 8;
-    static constexpr int SLOT_DOUBLES = FT * LDV;
+    static constexpr int SLOT_DOUBLES = PFT * LDV;
     static constexpr int SLOT_BYTES = SLOT_DOUBLES * 8;
     static constexpr int MISC_BYTES = 512;     // mbarriers
-    static constexpr int EXP_BYTES = MAX_SLOTS * FT * 4;
+    static constexpr int EXP_BYTES = MAX_SLOTS * PFT * 4;
     __host__ __device__ static constexpr int ring_bytes(int stages) { return stages * STAGE_BYTES; }
-    __host__ __device__ static constexpr int fixed_bytes(int slots, int stages) { return ring_bytes(stages) + slots * SLOT_BYTES + CNT_CAP_BYTES + MISC_BYTES + EXP_BYTES; }
-    // ops_bytes: per-group copies of the resolved op list (0 = read the ops from global memory)
-    __host__ __device__ static constexpr int total_bytes(int slots, int stages, int ops_bytes) { return fixed_bytes(slots, stages) + ops_bytes; }
+    __host__ __device__ static constexpr int total_bytes(int slots, int stages) { return ring_bytes(stages) + slots * SLOT_BYTES + PRUNE_CNT_CAP_BYTES + MISC_BYTES + EXP_BYTES; }
     __host__ static int max_slots(int smem_limit, int stages)
     {
-        int s = (smem_limit - ring_bytes(stages) - CNT_CAP_BYTES - MISC_BYTES - EXP_BYTES) / SLOT_BYTES;
+        int s = (smem_limit - ring_bytes(stages) - PRUNE_CNT_CAP_BYTES - MISC_BYTES - EXP_BYTES) / SLOT_BYTES;
         return s > MAX_SLOTS ? MAX_SLOTS : s;
     }
 };
@@ -73,31 +75,32 @@ __device__ __forceinline__ void group_sync(int group)
     asm volatile("bar.sync %0, %1;" ::"r"(group + 1), "n"(GROUP_THREADS) : "memory");
 }
 
-template <int MB>
-__global__ void __launch_bounds__(PRUNE2_THREADS, 1) prune_kernel(const PruneParams p)
+template <int MB, int NG>
+__global__ void __launch_bounds__(prune_threads(NG), 1) prune_kernel(const PruneParams p)
 {
-    using L = PruneSmem<MB>;
+    using L = PruneSmem<MB, NG>;
+    constexpr int PFT = L::PFT;
+    constexpr int CONSUMERS = NG * GROUP_WARPS;
     constexpr int NR = L::NR;
     constexpr int LDV = L::LDV;
     extern __shared__ __align__(128) unsigned char smem_raw[];
     double* ring = reinterpret_cast<double*>(smem_raw);
-    const int ring_bytes = L::ring_bytes(GROUPS * p.n_stages);      // p.n_stages = ring depth of ONE group
+    const int ring_bytes = L::ring_bytes(p.n_stages);
     const uint32_t stage_mask = (uint32_t)p.n_stages - 1u;
     double* slots = reinterpret_cast<double*>(smem_raw + ring_bytes);
     uint16_t* cnt_s = reinterpret_cast<uint16_t*>(smem_raw + ring_bytes + p.n_slots * L::SLOT_BYTES);
-    uint64_t* full_bar = reinterpret_cast<uint64_t*>(smem_raw + ring_bytes + p.n_slots * L::SLOT_BYTES + CNT_CAP_BYTES);
+    uint64_t* full_bar = reinterpret_cast<uint64_t*>(smem_raw + ring_bytes + p.n_slots * L::SLOT_BYTES + PRUNE_CNT_CAP_BYTES);
     uint64_t* empty_bar = full_bar + MAX_STAGES;
-    int* slot_exp = reinterpret_cast<int*>(smem_raw + ring_bytes + p.n_slots * L::SLOT_BYTES + CNT_CAP_BYTES + L::MISC_BYTES);
-    POp* ops_s = reinterpret_cast<POp*>(smem_raw + L::fixed_bytes(p.n_slots, GROUPS * p.n_stages));
+    int* slot_exp = reinterpret_cast<int*>(smem_raw + ring_bytes + p.n_slots * L::SLOT_BYTES + PRUNE_CNT_CAP_BYTES + L::MISC_BYTES);
 
     const int tid = threadIdx.x;
     const int warp = tid >> 5;
     const int lane = tid & 31;
 
     if (tid == 0) {
-        for (int s = 0; s < GROUPS * p.n_stages; ++s) {
+        for (int s = 0; s < p.n_stages; ++s) {
             mbar_init(&full_bar[s], 1);
-            mbar_init(&empty_bar[s], GROUP_WARPS);
+            mbar_init(&empty_bar[s], CONSUMERS);          // a stage is released when every consumer warp has read it
         }
         fence_barrier_init();
     }
@@ -105,18 +108,12 @@ __global__ void __launch_bounds__(PRUNE2_THREADS, 1) prune_kernel(const PrunePar
 
     const int64_t n_items = p.n_tiles * p.n_categories;
 
-    const int64_t vstride = (int64_t)gridDim.x * GROUPS;
-
-    if (warp >= CONSUMER_WARPS) {
-        // ===== producers: warp (group, lane_of_group) streams chunks pos = lane_of_group (mod PRODUCERS_PER_GROUP) =====
-        const int group = (warp - CONSUMER_WARPS) / PRODUCERS_PER_GROUP;
-        const int which = (warp - CONSUMER_WARPS) % PRODUCERS_PER_GROUP;
+    if (warp >= CONSUMERS) {
+        // ===== producers: stream the matrix K-chunks of every GEMM op of every item into the ring, alternate chunks each =====
+        const int which = warp - CONSUMERS;
         if (lane == 0) {
-            double* gring = ring + (size_t)group * p.n_stages * L::STAGE_DOUBLES;
-            uint64_t* gfull = full_bar + group * p.n_stages;
-            uint64_t* gempty = empty_bar + group * p.n_stages;
             uint32_t pos = 0;
-            for (int64_t item = (int64_t)blockIdx.x * GROUPS + group; item < n_items; item += vstride) {
+            for (int64_t item = blockIdx.x; item < n_items; item += gridDim.x) {
                 const int cat = (int)(item / p.n_tiles);
                 const POp* ops = p.ops + (size_t)cat * p.n_ops;
                 for (int o = 0; o < p.n_ops; ++o) {
@@ -124,12 +121,12 @@ __global__ void __launch_bounds__(PRUNE2_THREADS, 1) prune_kernel(const PrunePar
                     if (type != OP_GEMM_SET && type != OP_GEMM_MUL && type != OP_GEMM_SET_LEAF && type != OP_GEMM_MUL_LEAF) continue;
                     const double* src = p.mp + (size_t)ops[o].mat * p.mp_stride;
                     for (int ch = 0; ch < p.n_kchunks; ++ch, ++pos) {
-                        if ((int)(pos % PRODUCERS_PER_GROUP) != which) continue;
+                        if ((int)(pos % PRODUCER_WARPS) != which) continue;
                         const uint32_t stage = pos & stage_mask;
                         const uint32_t round = pos >> p.stage_shift;
-                        mbar_wait(&gempty[stage], (round & 1) ^ 1);
-                        mbar_arrive_expect_tx(&gfull[stage], L::STAGE_BYTES);
-                        bulk_copy_g2s(gring + (size_t)stage * L::STAGE_DOUBLES, src + (size_t)ch * L::STAGE_DOUBLES, L::STAGE_BYTES, &gfull[stage]);
+                        mbar_wait(&empty_bar[stage], (round & 1) ^ 1);
+                        mbar_arrive_expect_tx(&full_bar[stage], L::STAGE_BYTES);
+                        bulk_copy_g2s(ring + (size_t)stage * L::STAGE_DOUBLES, src + (size_t)ch * L::STAGE_DOUBLES, L::STAGE_BYTES, &full_bar[stage]);
                     }
                 }
             }
@@ -138,24 +135,26 @@ __global__ void __launch_bounds__(PRUNE2_THREADS, 1) prune_kernel(const PrunePar
     }
 
     // =============================== consumers =====================================================
-    const int group = warp / GROUP_WARPS;         // family half of the tile: columns [group*16, +16)
+    const int group = warp / GROUP_WARPS;         // families [group*16, +16) of the tile
     const int wg = warp % GROUP_WARPS;            // row group: rows [wg*8*MB, +8*MB)
     const int gtid = tid - group * GROUP_THREADS; // thread index inside the group
     const int g = lane >> 2;                      // fragment row / column group
     const int t4 = lane & 3;
     const int fbase = group * GFT;                // first tile family of this group
     uint32_t pos = 0;
-    int ops_cat = -1;
-    ring += (size_t)group * p.n_stages * L::STAGE_DOUBLES;      // this group's half of the ring
-    full_bar += group * p.n_stages;
-    empty_bar += group * p.n_stages;
-    POp* my_ops = ops_s + (size_t)group * p.n_ops;
     uint16_t* my_cnt = cnt_s + (size_t)fbase * p.n_leaves;
 
-    for (int64_t item = (int64_t)blockIdx.x * GROUPS + group; item < n_items; item += vstride) {
+    // One-time stagger: the groups run the same op list at the same speed, so the phase difference they start with
+    // persists (up to the ring depth); started together they would all sit between two GEMMs at the same time.
+    if (group > 0 && p.stagger_cycles > 0) {
+        const long long t0 = clock64(), d = (long long)group * p.stagger_cycles;
+        while (clock64() - t0 < d) { }
+    }
+
+    for (int64_t item = blockIdx.x; item < n_items; item += gridDim.x) {
         const int cat = (int)(item / p.n_tiles);
         const int64_t tile = item % p.n_tiles;
-        const int64_t fam0 = tile * GFT;          // first family of this group's tile
+        const int64_t fam0 = tile * PFT + fbase;  // first family of this group
 
         group_sync(group);      // previous item fully finished with this group's shared memory
         if (p.counts_in_smem) {
@@ -167,20 +166,15 @@ __global__ void __launch_bounds__(PRUNE2_THREADS, 1) prune_kernel(const PrunePar
                 my_cnt[i] = (uint16_t)p.counts[fam * p.n_leaves + (i - f * p.n_leaves)];
             }
         }
-        if (p.ops_in_smem && cat != ops_cat) {
-            const int4* src = reinterpret_cast<const int4*>(p.ops + (size_t)cat * p.n_ops);
-            int4* dst = reinterpret_cast<int4*>(my_ops);
-            for (int i = gtid; i < 2 * p.n_ops; i += GROUP_THREADS) dst[i] = src[i];
-            ops_cat = cat;
-        }
-        if (gtid < MAX_SLOTS * GFT) slot_exp[(gtid / GFT) * FT + fbase + (gtid % GFT)] = 0;
+        if (gtid < MAX_SLOTS * GFT) slot_exp[(gtid / GFT) * PFT + fbase + (gtid % GFT)] = 0;
         group_sync(group);
 
+        // the (L2-resident, 32-byte) ops are fetched one ahead: the load latency hides behind the current op
         const POp* gops = p.ops + (size_t)cat * p.n_ops;
+        POp next_op = gops[0];
         for (int o = 0; o < p.n_ops; ++o) {
-            POp op;
-            if (p.ops_in_smem) op = my_ops[o];
-            else op = gops[o];
+            const POp op = next_op;
+            if (o + 1 < p.n_ops) next_op = gops[o + 1];
             switch (op.type) {
             case OP_LEAF_SET2: {
                 // ---- a cherry in one pass: V = column(leaf 1) * column(leaf 2) ----
@@ -210,7 +204,7 @@ __global__ void __launch_bounds__(PRUNE2_THREADS, 1) prune_kernel(const PrunePar
                     double* row = dst + (size_t)f * LDV;
                     #pragma unroll
                     for (int i = 0; i < MB; ++i) row[lane + 32 * i] = v1[fi][i] * v2[fi][i];
-                    if (lane == 0) slot_exp[op.a * FT + f] = 0;
+                    if (lane == 0) slot_exp[op.a * PFT + f] = 0;
                 }
                 group_sync(group);
                 break;
@@ -257,7 +251,7 @@ __global__ void __launch_bounds__(PRUNE2_THREADS, 1) prune_kernel(const PrunePar
                     if (op.type == OP_LEAF_SET) {
                         #pragma unroll
                         for (int i = 0; i < MB; ++i) row[lane + 32 * i] = v[i];
-                        if (lane == 0) slot_exp[op.a * FT + f] = 0;     // fresh vector in a recycled slot
+                        if (lane == 0) slot_exp[op.a * PFT + f] = 0;     // fresh vector in a recycled slot
                     }
                     else {
                         #pragma unroll
@@ -277,31 +271,8 @@ __global__ void __launch_bounds__(PRUNE2_THREADS, 1) prune_kernel(const PrunePar
                 const int src_slot = is_set ? op.a : op.b;
                 const double* vsrc = slots + (size_t)src_slot * L::SLOT_DOUBLES + (size_t)(fbase + g) * LDV + t4;
                 double acc[MB][2][2];
-                double lf[MB][2][2];       // leaf-sibling factor of each output element (1.0 when there is none)
                 #pragma unroll
-                for (int i = 0; i < MB; ++i) {
-                    acc[i][0][0] = acc[i][0][1] = acc[i][1][0] = acc[i][1][1] = 0.0;
-                    lf[i][0][0] = lf[i][0][1] = lf[i][1][0] = lf[i][1][1] = 1.0;
-                }
-                if (with_leaf) {
-                    // issued before the K loop so the L2 latency of the gather hides behind the MMAs
-                    const double* mt2 = p.mt + (size_t)op.mat2 * p.mt_stride + wg * 8 * MB + g;
-                    #pragma unroll
-                    for (int nb = 0; nb < 2; ++nb)
-                        #pragma unroll
-                        for (int e = 0; e < 2; ++e) {
-                            const int fl = nb * 8 + t4 * 2 + e;
-                            int obs;
-                            if (p.counts_in_smem) obs = my_cnt[fl * p.n_leaves + op.col2];
-                            else {
-                                int64_t fam = fam0 + fl;
-                                if (fam >= p.n_families) fam = p.n_families - 1;
-                                obs = p.counts[fam * p.n_leaves + op.col2];
-                            }
-                            #pragma unroll
-                            for (int i = 0; i < MB; ++i) lf[i][nb][e] = __ldg(mt2 + (size_t)obs * NR + i * 8);
-                        }
-                }
+                for (int i = 0; i < MB; ++i) acc[i][0][0] = acc[i][0][1] = acc[i][1][0] = acc[i][1][1] = 0.0;
                 // Fragments are double-buffered in registers: the loads of panel q+1 (possibly from the next
                 // ring stage) are issued before the MMAs of panel q, so shared-memory latency never gates the pipe.
                 const int a_off = (wg * 8 * MB) * 4 + lane;
@@ -351,6 +322,28 @@ __global__ void __launch_bounds__(PRUNE2_THREADS, 1) prune_kernel(const PrunePar
                     stage = nstage;
                     pos = npos;
                 }
+                double lf[MB][2][2];       // leaf-sibling factor of each output element (1.0 when there is none)
+                #pragma unroll
+                for (int i = 0; i < MB; ++i) lf[i][0][0] = lf[i][0][1] = lf[i][1][0] = lf[i][1][1] = 1.0;
+                if (with_leaf) {
+                    // gathered after the K loop (the fragment registers are free now); the other groups' MMAs cover the L2 latency
+                    const double* mt2 = p.mt + (size_t)op.mat2 * p.mt_stride + wg * 8 * MB + g;
+                    #pragma unroll
+                    for (int nb = 0; nb < 2; ++nb)
+                        #pragma unroll
+                        for (int e = 0; e < 2; ++e) {
+                            const int fl = nb * 8 + t4 * 2 + e;
+                            int obs;
+                            if (p.counts_in_smem) obs = my_cnt[fl * p.n_leaves + op.col2];
+                            else {
+                                int64_t fam = fam0 + fl;
+                                if (fam >= p.n_families) fam = p.n_families - 1;
+                                obs = p.counts[fam * p.n_leaves + op.col2];
+                            }
+                            #pragma unroll
+                            for (int i = 0; i < MB; ++i) lf[i][nb][e] = __ldg(mt2 + (size_t)obs * NR + i * 8);
+                        }
+                }
                 if (is_set) group_sync(group);      // in place: every warp of the group is done reading V_child before anyone overwrites it
                 double* dst = slots + (size_t)op.a * L::SLOT_DOUBLES;
                 #pragma unroll
@@ -367,7 +360,7 @@ __global__ void __launch_bounds__(PRUNE2_THREADS, 1) prune_kernel(const PrunePar
                         else { *q0 *= y0; *q1 *= y1; }
                     }
                 }
-                if (!is_set && p.rescale && gtid < GFT) slot_exp[op.a * FT + fbase + gtid] += slot_exp[op.b * FT + fbase + gtid];
+                if (!is_set && p.rescale && gtid < GFT) slot_exp[op.a * PFT + fbase + gtid] += slot_exp[op.b * PFT + fbase + gtid];
                 group_sync(group);
                 break;
             }
@@ -376,14 +369,14 @@ __global__ void __launch_bounds__(PRUNE2_THREADS, 1) prune_kernel(const PrunePar
                 // this group's half of the slot (families fbase .. fbase+GFT-1 are contiguous rows)
                 double* sl = slots + (size_t)op.a * L::SLOT_DOUBLES + (size_t)fbase * LDV;
                 double* sc = p.scratch + ((size_t)blockIdx.x * p.n_spill + op.b) * L::SLOT_DOUBLES + (size_t)fbase * LDV;
-                int* sce = p.scratch_exp + ((size_t)blockIdx.x * p.n_spill + op.b) * FT + fbase;
+                int* sce = p.scratch_exp + ((size_t)blockIdx.x * p.n_spill + op.b) * PFT + fbase;
                 if (op.type == OP_SPILL) {
                     for (int i = gtid; i < GFT * LDV; i += GROUP_THREADS) sc[i] = sl[i];
-                    if (gtid < GFT) sce[gtid] = slot_exp[op.a * FT + fbase + gtid];
+                    if (gtid < GFT) sce[gtid] = slot_exp[op.a * PFT + fbase + gtid];
                 }
                 else {
                     for (int i = gtid; i < GFT * LDV; i += GROUP_THREADS) sl[i] = sc[i];
-                    if (gtid < GFT) slot_exp[op.a * FT + fbase + gtid] = sce[gtid];
+                    if (gtid < GFT) slot_exp[op.a * PFT + fbase + gtid] = sce[gtid];
                 }
                 group_sync(group);
                 break;
@@ -405,7 +398,7 @@ __global__ void __launch_bounds__(PRUNE2_THREADS, 1) prune_kernel(const PrunePar
                         frexp(m, &e);                       // m = f * 2^e, f in [0.5, 1)
                         const double sc = ldexp(1.0, -e);   // exact; brings the max into [0.5, 1)
                         for (int s = lane; s < NR; s += 32) row[s] *= sc;
-                        if (lane == 0) slot_exp[op.a * FT + f] += e;
+                        if (lane == 0) slot_exp[op.a * PFT + f] += e;
                     }
                 }
                 group_sync(group);
@@ -421,7 +414,7 @@ __global__ void __launch_bounds__(PRUNE2_THREADS, 1) prune_kernel(const PrunePar
                     const int64_t fam = fam0 + fl;
                     if (fam >= p.n_families) continue;      // warp-uniform
                     const double* row = sl + (size_t)f * LDV;
-                    const int e = p.rescale ? slot_exp[op.a * FT + f] : 0;
+                    const int e = p.rescale ? slot_exp[op.a * PFT + f] : 0;
                     if (p.root_out) {
                         double* out = p.root_out + ((size_t)fam * p.n_categories + cat) * p.mrf;
                         for (int j = lane; j < p.mrf; j += 32) out[j] = e ? ldexp(row[j + 1], e) : row[j + 1];

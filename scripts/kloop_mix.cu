@@ -1,0 +1,277 @@
+// Which ingredient of the pruning kernel's K loop costs FP64 tensor throughput?  The loop is rebuilt here from its
+// parts, switched on one at a time (flags), with the kernel's geometry: 2 consumer groups x 4 warps (one warp per
+// sub-partition each), 40 x 16 warp tiles (10 DMMA per K panel, 7 LDS.64), 2 panels per ring stage, 19 stages per
+// GEMM, fragments double-buffered in registers.
+//   BAR   per stage: mbarrier wait on "full" before the loads, arrive on "empty" after the MMAs; producer warp(s)
+//         answer each "empty" with a plain arrive on "full"
+//   COPY  the producer issues the real 10 KB bulk copy (cp.async.bulk + complete_tx) instead
+//   GEMM  every 19 stages: group barrier, 20 STS.64 per thread (the epilogue's stores), group barrier, accumulators reset
+//   DMUL  the epilogue is the kernel's read-modify-write child product: dst *= acc * factor (40 FP64 multiplies per thread)
+//   LEAF  after every GEMM a leaf gather: 20 doubles per thread from an L2-resident table (address from a shared-memory
+//         count), stored to the slot, group barrier — the kernel's leaf / cherry ops at L2 latency
+//   XBLK  the wait for the next stage is a try_wait issued BEFORE the ten MMAs of panel 0 and branched on after them
+//   PREF  the leaf gather's loads are issued BEFORE the K loop of the preceding GEMM (20 doubles in registers) and stored after it
+//   G3    three consumer groups (12 consumer warps, 48 families) on the shared ring instead of two
+//   SHARED  one 8-stage ring consumed by both groups (released by 8 warps) instead of a 4-stage ring per group
+// Prints TFLOP/s per configuration.  Build: nvcc -gencode arch=compute_100a,code=sm_100a -O3 -o kloop_mix.bin.so kloop_mix.cu
+#include <cstdint>
+#include <cstdio>
+#include <cstdlib>
+#include <algorithm>
+#include <cuda_runtime.h>
+
+#define CK(x) do { cudaError_t e = (x); if (e != cudaSuccess) { fprintf(stderr, "%s: %s\n", #x, cudaGetErrorString(e)); exit(1); } } while (0)
+
+constexpr int F_BAR = 1, F_COPY = 2, F_GEMM = 4, F_SHARED = 8, F_DMUL = 16, F_LEAF = 32, F_XBLK = 64, F_PREF = 128, F_G3 = 256;
+constexpr int STAGE_BYTES = 10240, NKC = 19, GEMMS = 256, LDV = 164;
+
+__device__ __forceinline__ uint32_t s32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
+__device__ __forceinline__ void dmma(double& d0, double& d1, double a, double b)
+{
+    asm volatile("mma.sync.aligned.m8n8k4.row.col.f64.f64.f64.f64 {%0,%1}, {%2}, {%3}, {%0,%1};" : "+d"(d0), "+d"(d1) : "d"(a), "d"(b));
+}
+__device__ __forceinline__ double lds64(uint32_t addr) { double v; asm volatile("ld.shared.f64 %0, [%1];" : "=d"(v) : "r"(addr)); return v; }
+__device__ __forceinline__ void mbar_init(uint64_t* b, uint32_t c) { asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(s32(b)), "r"(c)); }
+__device__ __forceinline__ void mbar_arrive(uint64_t* b) { asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(s32(b)) : "memory"); }
+__device__ __forceinline__ void mbar_expect(uint64_t* b, uint32_t n) { asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(s32(b)), "r"(n) : "memory"); }
+__device__ __forceinline__ void mbar_wait(uint64_t* b, uint32_t parity)
+{
+    asm volatile("{\n.reg .pred p;\nW:\nmbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n@p bra D;\nbra W;\nD:\n}\n" ::"r"(s32(b)), "r"(parity) : "memory");
+}
+__device__ __forceinline__ void bulk(void* dst, const void* src, uint32_t bytes, uint64_t* bar)
+{
+    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(s32(dst)), "l"(src), "r"(bytes), "r"(s32(bar)) : "memory");
+}
+
+__device__ __forceinline__ void dmma_x10_then_wait(double (&c)[5][2][2], const double (&a)[5], double b0, double b1, uint64_t* bar, uint32_t parity)
+{
+    asm volatile(
+        "{\n"
+        ".reg .pred p;\n"
+        "mbarrier.try_wait.parity.shared::cta.b64 p, [%27], %28;\n"
+        "mma.sync.aligned.m8n8k4.row.col.f64.f64.f64.f64 {%0,%1}, {%20}, {%25}, {%0,%1};\n"
+        "mma.sync.aligned.m8n8k4.row.col.f64.f64.f64.f64 {%2,%3}, {%20}, {%26}, {%2,%3};\n"
+        "mma.sync.aligned.m8n8k4.row.col.f64.f64.f64.f64 {%4,%5}, {%21}, {%25}, {%4,%5};\n"
+        "mma.sync.aligned.m8n8k4.row.col.f64.f64.f64.f64 {%6,%7}, {%21}, {%26}, {%6,%7};\n"
+        "mma.sync.aligned.m8n8k4.row.col.f64.f64.f64.f64 {%8,%9}, {%22}, {%25}, {%8,%9};\n"
+        "mma.sync.aligned.m8n8k4.row.col.f64.f64.f64.f64 {%10,%11}, {%22}, {%26}, {%10,%11};\n"
+        "mma.sync.aligned.m8n8k4.row.col.f64.f64.f64.f64 {%12,%13}, {%23}, {%25}, {%12,%13};\n"
+        "mma.sync.aligned.m8n8k4.row.col.f64.f64.f64.f64 {%14,%15}, {%23}, {%26}, {%14,%15};\n"
+        "mma.sync.aligned.m8n8k4.row.col.f64.f64.f64.f64 {%16,%17}, {%24}, {%25}, {%16,%17};\n"
+        "mma.sync.aligned.m8n8k4.row.col.f64.f64.f64.f64 {%18,%19}, {%24}, {%26}, {%18,%19};\n"
+        "@p bra X10_DONE;\n"
+        "X10_WAIT:\n"
+        "mbarrier.try_wait.parity.shared::cta.b64 p, [%27], %28;\n"
+        "@!p bra X10_WAIT;\n"
+        "X10_DONE:\n"
+        "}\n"
+        : "+d"(c[0][0][0]), "+d"(c[0][0][1]), "+d"(c[0][1][0]), "+d"(c[0][1][1]), "+d"(c[1][0][0]), "+d"(c[1][0][1]), "+d"(c[1][1][0]),
+          "+d"(c[1][1][1]), "+d"(c[2][0][0]), "+d"(c[2][0][1]), "+d"(c[2][1][0]), "+d"(c[2][1][1]), "+d"(c[3][0][0]), "+d"(c[3][0][1]),
+          "+d"(c[3][1][0]), "+d"(c[3][1][1]), "+d"(c[4][0][0]), "+d"(c[4][0][1]), "+d"(c[4][1][0]), "+d"(c[4][1][1])
+        : "d"(a[0]), "d"(a[1]), "d"(a[2]), "d"(a[3]), "d"(a[4]), "d"(b0), "d"(b1), "r"(s32(bar)), "r"(parity)
+        : "memory");
+}
+
+
+template <int FLAGS>
+__global__ void __launch_bounds__((FLAGS & 256) ? 448 : 384, 1) kloop_kernel(const double* __restrict__ mats, double* out)
+{
+    extern __shared__ __align__(128) unsigned char smem[];
+    double* ring = reinterpret_cast<double*>(smem);                              // 8 stages x 10 KB
+    double* slot = reinterpret_cast<double*>(smem + 8 * STAGE_BYTES);            // 48 families x LDV doubles
+    uint64_t* full = reinterpret_cast<uint64_t*>(smem + 8 * STAGE_BYTES + 48 * LDV * 8);
+    uint64_t* empty = full + 8;
+    const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+    constexpr bool SHARED = FLAGS & F_SHARED;
+    constexpr int NG = (FLAGS & F_G3) ? 3 : 2;
+    constexpr int CW = NG * 4;                                                   // consumer warps
+    static_assert(!(FLAGS & F_G3) || (FLAGS & F_SHARED), "three groups share the ring");
+    constexpr int DEPTH = SHARED ? 8 : 4;                                        // stages seen by one group
+    for (int i = tid; i < 8 * STAGE_BYTES / 8 + 48 * LDV; i += blockDim.x) ring[i] = 1.0 + 1e-9 * i;
+    if (tid == 0) {
+        for (int s = 0; s < 8; ++s) { mbar_init(&full[s], 1); mbar_init(&empty[s], SHARED ? CW : 4); }
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    }
+    __syncthreads();
+    const int total = GEMMS * NKC;
+
+    if (warp >= CW) {
+        // producers: warps 8,9 -> group 0 (or the shared ring), 10,11 -> group 1; alternate chunks
+        if (!(FLAGS & F_BAR)) return;
+        const int grp = SHARED ? 0 : (warp - CW) / 2, which = (warp - CW) % 2;
+        if (SHARED && warp >= CW + 2) return;
+        if (lane == 0) {
+            uint64_t* f = full + grp * 4; uint64_t* e = empty + grp * 4; double* r = ring + (size_t)grp * 4 * STAGE_BYTES / 8;
+            for (int pos = which; pos < total; pos += 2) {
+                const int st = pos % DEPTH, round = pos / DEPTH;
+                mbar_wait(&e[st], (round & 1) ^ 1);
+                if (FLAGS & F_COPY) {
+                    mbar_expect(&f[st], STAGE_BYTES);
+                    bulk(r + (size_t)st * STAGE_BYTES / 8, mats + ((size_t)(blockIdx.x * 7 + pos) % 2048) * (STAGE_BYTES / 8), STAGE_BYTES, &f[st]);
+                }
+                else mbar_arrive(&f[st]);
+            }
+        }
+        return;
+    }
+
+    const int group = warp / 4, wg = warp % 4, g = lane >> 2, t4 = lane & 3;
+    uint64_t* f = full + (SHARED ? 0 : group * 4);
+    uint64_t* e = empty + (SHARED ? 0 : group * 4);
+    const uint32_t ring_u = s32(ring) + (SHARED ? 0 : group * 4 * STAGE_BYTES) + (uint32_t)((wg * 40) * 4 + lane) * 8u;
+    const uint32_t v_u = s32(slot) + (uint32_t)((group * 16 + g) * LDV + t4) * 8u;
+    constexpr uint32_t NB1 = 8u * LDV * 8u, P1 = 160 * 32u;
+    double acc[5][2][2];
+    for (int i = 0; i < 5; ++i) acc[i][0][0] = acc[i][0][1] = acc[i][1][0] = acc[i][1][1] = 0.0;
+    double a0[5], a1[5], b00, b01, b10, b11;
+    int pos = 0;
+    double sink = 0;
+    #pragma unroll 1
+    for (int gemm = 0; gemm < GEMMS; ++gemm) {
+        double pv[4][5];
+        if ((FLAGS & F_LEAF) && (FLAGS & F_PREF)) {
+            #pragma unroll
+            for (int fi = 0; fi < 4; ++fi) {
+                const int obs = (int)(slot[(group * 16 + wg * 4 + fi) * LDV + 3] * 37.0 + gemm) % 150;
+                #pragma unroll
+                for (int i = 0; i < 5; ++i) pv[fi][i] = __ldg(mats + ((size_t)((blockIdx.x * 3 + gemm) % 198) * 151 + obs) * 160 + lane + 32 * i);
+            }
+        }
+        int st = pos % DEPTH;
+        if (FLAGS & F_BAR) mbar_wait(&f[st], (pos / DEPTH) & 1);
+        #pragma unroll
+        for (int i = 0; i < 5; ++i) a0[i] = lds64(ring_u + st * STAGE_BYTES + i * 256u);
+        b00 = lds64(v_u); b01 = lds64(v_u + NB1);
+        #pragma unroll 1
+        for (int ch = 0; ch < NKC; ++ch) {
+            const uint32_t sa = ring_u + st * STAGE_BYTES, vb = v_u + ch * 64;
+            #pragma unroll
+            for (int i = 0; i < 5; ++i) a1[i] = lds64(sa + P1 + i * 256u);
+            b10 = lds64(vb + 32u); b11 = lds64(vb + NB1 + 32u);
+            const int npos = pos + 1, nst = npos % DEPTH;
+            if ((FLAGS & F_XBLK) && (FLAGS & F_BAR)) {
+                const bool more = ch + 1 < NKC;
+                dmma_x10_then_wait(acc, a0, b00, b01, &f[more ? nst : st], ((more ? npos : pos) / DEPTH) & 1);
+            }
+            else {
+                #pragma unroll
+                for (int i = 0; i < 5; ++i) { dmma(acc[i][0][0], acc[i][0][1], a0[i], b00); dmma(acc[i][1][0], acc[i][1][1], a0[i], b01); }
+            }
+            if (ch + 1 < NKC) {
+                if ((FLAGS & F_BAR) && !(FLAGS & F_XBLK)) mbar_wait(&f[nst], (npos / DEPTH) & 1);
+                #pragma unroll
+                for (int i = 0; i < 5; ++i) a0[i] = lds64(ring_u + nst * STAGE_BYTES + i * 256u);
+                b00 = lds64(vb + 64u); b01 = lds64(vb + NB1 + 64u);
+            }
+            #pragma unroll
+            for (int i = 0; i < 5; ++i) { dmma(acc[i][0][0], acc[i][0][1], a1[i], b10); dmma(acc[i][1][0], acc[i][1][1], a1[i], b11); }
+            if (FLAGS & F_BAR) { __syncwarp(); if (lane == 0) mbar_arrive(&e[st]); }
+            st = nst; pos = npos;
+        }
+        if (FLAGS & F_GEMM) {
+            asm volatile("bar.sync %0, 128;" ::"r"(group + 1) : "memory");
+            double* dst = slot + (size_t)(group * 16 + t4 * 2) * LDV + wg * 40 + g;
+            #pragma unroll
+            for (int i = 0; i < 5; ++i)
+                #pragma unroll
+                for (int nb = 0; nb < 2; ++nb) {
+                    if (FLAGS & F_DMUL) {
+                        const double y0 = (1.0 + 1e-20 * acc[i][nb][0]) * (1.0 + 1e-18 * b00), y1 = (1.0 + 1e-20 * acc[i][nb][1]) * (1.0 + 1e-18 * b01);
+                        dst[(nb * 8) * LDV + i * 8] *= y0;
+                        dst[(nb * 8 + 1) * LDV + i * 8] *= y1;
+                    }
+                    else {
+                        dst[(nb * 8) * LDV + i * 8] = 1.0 + 1e-20 * acc[i][nb][0];
+                        dst[(nb * 8 + 1) * LDV + i * 8] = 1.0 + 1e-20 * acc[i][nb][1];
+                    }
+                    sink += acc[i][nb][0];
+                    acc[i][nb][0] = acc[i][nb][1] = 0.0;
+                }
+            asm volatile("bar.sync %0, 128;" ::"r"(group + 1) : "memory");
+        }
+        if ((FLAGS & F_LEAF) && !(FLAGS & F_PREF)) {
+            double v[4][5];
+            #pragma unroll
+            for (int fi = 0; fi < 4; ++fi) {
+                const int obs = (int)(slot[(group * 16 + wg * 4 + fi) * LDV + 3] * 37.0 + gemm) % 150;
+                #pragma unroll
+                for (int i = 0; i < 5; ++i) v[fi][i] = __ldg(mats + ((size_t)((blockIdx.x * 3 + gemm) % 198) * 151 + obs) * 160 + lane + 32 * i);
+            }
+            #pragma unroll
+            for (int fi = 0; fi < 4; ++fi)
+                #pragma unroll
+                for (int i = 0; i < 5; ++i) slot[(group * 16 + wg * 4 + fi) * LDV + lane + 32 * i] = 1.0 + 1e-20 * v[fi][i];
+            asm volatile("bar.sync %0, 128;" ::"r"(group + 1) : "memory");
+        }
+        if ((FLAGS & F_LEAF) && (FLAGS & F_PREF)) {
+            #pragma unroll
+            for (int fi = 0; fi < 4; ++fi)
+                #pragma unroll
+                for (int i = 0; i < 5; ++i) slot[(group * 16 + wg * 4 + fi) * LDV + lane + 32 * i] = 1.0 + 1e-20 * pv[fi][i];
+            asm volatile("bar.sync %0, 128;" ::"r"(group + 1) : "memory");
+        }
+    }
+    for (int i = 0; i < 5; ++i) sink += acc[i][0][0] + acc[i][0][1] + acc[i][1][0] + acc[i][1][1];
+    if (sink == 12345.678) out[0] = sink;
+}
+
+template <int FLAGS>
+double run(int sms, const double* mats, double* out)
+{
+    const size_t smem = 8 * STAGE_BYTES + 48 * LDV * 8 + 256;
+    constexpr int NG = (FLAGS & F_G3) ? 3 : 2;
+    const int threads = (NG * 4 + 4) * 32 > 448 ? 448 : (NG == 3 ? 448 : 384);
+    CK(cudaFuncSetAttribute(kloop_kernel<FLAGS>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    cudaEvent_t e0, e1;
+    CK(cudaEventCreate(&e0)); CK(cudaEventCreate(&e1));
+    kloop_kernel<FLAGS><<<sms, threads, smem>>>(mats, out);
+    CK(cudaGetLastError());
+    CK(cudaDeviceSynchronize());
+    double best = 1e30;
+    for (int r = 0; r < 3; ++r) {
+        CK(cudaEventRecord(e0));
+        kloop_kernel<FLAGS><<<sms, threads, smem>>>(mats, out);
+        CK(cudaEventRecord(e1));
+        CK(cudaEventSynchronize(e1));
+        float ms; CK(cudaEventElapsedTime(&ms, e0, e1));
+        best = std::min(best, (double)ms);
+    }
+    const double flops = 2.0 * 8 * 8 * 4 * 20.0 * NKC * GEMMS * (double)sms * (NG * 4);
+    return flops / best / 1e9;
+}
+
+int main()
+{
+    int sms = 0;
+    CK(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, 0));
+    double *out, *mats;
+    CK(cudaMalloc(&out, 64));
+    const size_t mat_bytes = std::max((size_t)2048 * STAGE_BYTES, (size_t)198 * 151 * 160 * 8);
+    CK(cudaMalloc(&mats, mat_bytes));
+    CK(cudaMemset(mats, 0, mat_bytes));
+    printf("{\"sms\": %d", sms);
+    printf(", \"loop_only\": %.2f", run<0>(sms, mats, out));
+    printf(", \"bar\": %.2f", run<F_BAR>(sms, mats, out));
+    printf(", \"bar_copy\": %.2f", run<F_BAR | F_COPY>(sms, mats, out));
+    printf(", \"gemm\": %.2f", run<F_GEMM>(sms, mats, out));
+    printf(", \"bar_gemm\": %.2f", run<F_BAR | F_GEMM>(sms, mats, out));
+    printf(", \"bar_copy_gemm\": %.2f", run<F_BAR | F_COPY | F_GEMM>(sms, mats, out));
+    printf(", \"bar_copy_gemm_dmul\": %.2f", run<F_BAR | F_COPY | F_GEMM | F_DMUL>(sms, mats, out));
+    printf(", \"bar_copy_gemm_leaf\": %.2f", run<F_BAR | F_COPY | F_GEMM | F_LEAF>(sms, mats, out));
+    printf(", \"bar_copy_gemm_dmul_leaf\": %.2f", run<F_BAR | F_COPY | F_GEMM | F_DMUL | F_LEAF>(sms, mats, out));
+    printf(", \"shared_bar_copy_gemm_dmul_leaf\": %.2f", run<F_SHARED | F_BAR | F_COPY | F_GEMM | F_DMUL | F_LEAF>(sms, mats, out));
+    printf(", \"bar_xblk\": %.2f", run<F_BAR | F_XBLK>(sms, mats, out));
+    printf(", \"bar_copy_gemm_xblk\": %.2f", run<F_BAR | F_COPY | F_GEMM | F_XBLK>(sms, mats, out));
+    printf(", \"bar_copy_gemm_dmul_leaf_xblk\": %.2f", run<F_BAR | F_COPY | F_GEMM | F_DMUL | F_LEAF | F_XBLK>(sms, mats, out));
+    printf(", \"bar_copy_gemm_dmul_leaf_pref\": %.2f", run<F_BAR | F_COPY | F_GEMM | F_DMUL | F_LEAF | F_PREF>(sms, mats, out));
+    printf(", \"shared_all_pref\": %.2f", run<F_SHARED | F_BAR | F_COPY | F_GEMM | F_DMUL | F_LEAF | F_PREF>(sms, mats, out));
+    printf(", \"g3_bar_copy\": %.2f", run<F_G3 | F_SHARED | F_BAR | F_COPY>(sms, mats, out));
+    printf(", \"g3_bar_copy_gemm\": %.2f", run<F_G3 | F_SHARED | F_BAR | F_COPY | F_GEMM>(sms, mats, out));
+    printf(", \"g3_all\": %.2f", run<F_G3 | F_SHARED | F_BAR | F_COPY | F_GEMM | F_DMUL | F_LEAF>(sms, mats, out));
+    printf(", \"g3_all_pref\": %.2f", run<F_G3 | F_SHARED | F_BAR | F_COPY | F_GEMM | F_DMUL | F_LEAF | F_PREF>(sms, mats, out));
+    printf(", \"shared_bar\": %.2f", run<F_SHARED | F_BAR>(sms, mats, out));
+    printf(", \"shared_bar_copy\": %.2f", run<F_SHARED | F_BAR | F_COPY>(sms, mats, out));
+    printf(", \"shared_bar_copy_gemm\": %.2f", run<F_SHARED | F_BAR | F_COPY | F_GEMM>(sms, mats, out));
+    printf("}\n");
+    return 0;
+}
