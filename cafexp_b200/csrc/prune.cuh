@@ -322,11 +322,13 @@ __global__ void __launch_bounds__(prune_threads(NG), 1) prune_kernel(const Prune
                     stage = nstage;
                     pos = npos;
                 }
-                double lf[MB][2][2];       // leaf-sibling factor of each output element (1.0 when there is none)
-                #pragma unroll
-                for (int i = 0; i < MB; ++i) lf[i][0][0] = lf[i][0][1] = lf[i][1][0] = lf[i][1][1] = 1.0;
+                // ---- epilogue, one FP64 multiply per element at most (none for a plain first factor): acc * 1.0 == acc
+                //      exactly, so skipping the unit leaf factor changes no bit, and FP64 multiplies share the pipe
+                //      with the other group's MMAs
+                double* dst = slots + (size_t)op.a * L::SLOT_DOUBLES + (size_t)(fbase + t4 * 2) * LDV + wg * 8 * MB + g;
                 if (with_leaf) {
-                    // gathered after the K loop (the fragment registers are free now); the other groups' MMAs cover the L2 latency
+                    // leaf-sibling factors, gathered after the K loop (the fragment registers are free now)
+                    double lf[MB][2][2];
                     const double* mt2 = p.mt + (size_t)op.mat2 * p.mt_stride + wg * 8 * MB + g;
                     #pragma unroll
                     for (int nb = 0; nb < 2; ++nb)
@@ -343,22 +345,47 @@ __global__ void __launch_bounds__(prune_threads(NG), 1) prune_kernel(const Prune
                             #pragma unroll
                             for (int i = 0; i < MB; ++i) lf[i][nb][e] = __ldg(mt2 + (size_t)obs * NR + i * 8);
                         }
-                }
-                if (is_set) group_sync(group);      // in place: every warp of the group is done reading V_child before anyone overwrites it
-                double* dst = slots + (size_t)op.a * L::SLOT_DOUBLES;
-                #pragma unroll
-                for (int i = 0; i < MB; ++i) {
-                    const int s = wg * 8 * MB + i * 8 + g;
+                    if (is_set) group_sync(group);      // in place: every warp of the group is done reading V_child before anyone overwrites it
                     #pragma unroll
-                    for (int nb = 0; nb < 2; ++nb) {
-                        const int f = fbase + nb * 8 + t4 * 2;
-                        double* q0 = dst + (size_t)f * LDV + s;
-                        double* q1 = q0 + LDV;
-                        const double y0 = acc[i][nb][0] * lf[i][nb][0];
-                        const double y1 = acc[i][nb][1] * lf[i][nb][1];
-                        if (is_set) { *q0 = y0; *q1 = y1; }
-                        else { *q0 *= y0; *q1 *= y1; }
-                    }
+                    for (int i = 0; i < MB; ++i)
+                        #pragma unroll
+                        for (int nb = 0; nb < 2; ++nb) {
+                            double* q0 = dst + (size_t)(nb * 8) * LDV + i * 8;
+                            const double y0 = acc[i][nb][0] * lf[i][nb][0];
+                            const double y1 = acc[i][nb][1] * lf[i][nb][1];
+                            if (is_set) { q0[0] = y0; q0[LDV] = y1; }
+                            else { q0[0] *= y0; q0[LDV] *= y1; }
+                        }
+                }
+                else if (is_set) {
+                    group_sync(group);                  // in place, as above
+                    #pragma unroll
+                    for (int i = 0; i < MB; ++i)
+                        #pragma unroll
+                        for (int nb = 0; nb < 2; ++nb) {
+                            double* q0 = dst + (size_t)(nb * 8) * LDV + i * 8;
+                            q0[0] = acc[i][nb][0];
+                            q0[LDV] = acc[i][nb][1];
+                        }
+                }
+                else {
+                    double old[MB][2][2];               // all loads first, then the multiplies back to back
+                    #pragma unroll
+                    for (int i = 0; i < MB; ++i)
+                        #pragma unroll
+                        for (int nb = 0; nb < 2; ++nb) {
+                            const double* q0 = dst + (size_t)(nb * 8) * LDV + i * 8;
+                            old[i][nb][0] = q0[0];
+                            old[i][nb][1] = q0[LDV];
+                        }
+                    #pragma unroll
+                    for (int i = 0; i < MB; ++i)
+                        #pragma unroll
+                        for (int nb = 0; nb < 2; ++nb) {
+                            double* q0 = dst + (size_t)(nb * 8) * LDV + i * 8;
+                            q0[0] = old[i][nb][0] * acc[i][nb][0];
+                            q0[LDV] = old[i][nb][1] * acc[i][nb][1];
+                        }
                 }
                 if (!is_set && p.rescale && gtid < GFT) slot_exp[op.a * PFT + fbase + gtid] += slot_exp[op.b * PFT + fbase + gtid];
                 group_sync(group);

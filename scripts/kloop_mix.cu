@@ -12,6 +12,7 @@
 //   XBLK  the wait for the next stage is a try_wait issued BEFORE the ten MMAs of panel 0 and branched on after them
 //   PREF  the leaf gather's loads are issued BEFORE the K loop of the preceding GEMM (20 doubles in registers) and stored after it
 //   G3    three consumer groups (12 consumer warps, 48 families) on the shared ring instead of two
+//   P     K panels per ring stage (2: 10 KB stages, 4: 20 KB stages and half as many barrier operations)
 //   SHARED  one 8-stage ring consumed by both groups (released by 8 warps) instead of a 4-stage ring per group
 // Prints TFLOP/s per configuration.  Build: nvcc -gencode arch=compute_100a,code=sm_100a -O3 -o kloop_mix.bin.so kloop_mix.cu
 #include <cstdint>
@@ -23,7 +24,7 @@
 #define CK(x) do { cudaError_t e = (x); if (e != cudaSuccess) { fprintf(stderr, "%s: %s\n", #x, cudaGetErrorString(e)); exit(1); } } while (0)
 
 constexpr int F_BAR = 1, F_COPY = 2, F_GEMM = 4, F_SHARED = 8, F_DMUL = 16, F_LEAF = 32, F_XBLK = 64, F_PREF = 128, F_G3 = 256;
-constexpr int STAGE_BYTES = 10240, NKC = 19, GEMMS = 256, LDV = 164;
+constexpr int PANEL_BYTES = 5120, NPANELS = 40, GEMMS = 256, LDV = 164;     // 40 K panels of 4 columns per GEMM (K = 160)
 
 __device__ __forceinline__ uint32_t s32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
 __device__ __forceinline__ void dmma(double& d0, double& d1, double a, double b)
@@ -73,27 +74,28 @@ __device__ __forceinline__ void dmma_x10_then_wait(double (&c)[5][2][2], const d
 }
 
 
-template <int FLAGS>
+template <int FLAGS, int P = 2>
 __global__ void __launch_bounds__((FLAGS & 256) ? 448 : 384, 1) kloop_kernel(const double* __restrict__ mats, double* out)
 {
     extern __shared__ __align__(128) unsigned char smem[];
     double* ring = reinterpret_cast<double*>(smem);                              // 8 stages x 10 KB
-    double* slot = reinterpret_cast<double*>(smem + 8 * STAGE_BYTES);            // 48 families x LDV doubles
-    uint64_t* full = reinterpret_cast<uint64_t*>(smem + 8 * STAGE_BYTES + 48 * LDV * 8);
+    double* slot = reinterpret_cast<double*>(smem + 80 * 1024);            // 48 families x LDV doubles
+    uint64_t* full = reinterpret_cast<uint64_t*>(smem + 80 * 1024 + 48 * LDV * 8);
     uint64_t* empty = full + 8;
     const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
     constexpr bool SHARED = FLAGS & F_SHARED;
+    constexpr int STAGE_BYTES = P * PANEL_BYTES, NKC = NPANELS / P, RING_STAGES = 80 * 1024 / STAGE_BYTES;
     constexpr int NG = (FLAGS & F_G3) ? 3 : 2;
     constexpr int CW = NG * 4;                                                   // consumer warps
     static_assert(!(FLAGS & F_G3) || (FLAGS & F_SHARED), "three groups share the ring");
-    constexpr int DEPTH = SHARED ? 8 : 4;                                        // stages seen by one group
-    for (int i = tid; i < 8 * STAGE_BYTES / 8 + 48 * LDV; i += blockDim.x) ring[i] = 1.0 + 1e-9 * i;
+    constexpr int DEPTH = SHARED ? RING_STAGES : RING_STAGES / 2;                // stages seen by one group
+    for (int i = tid; i < 80 * 1024 / 8 + 48 * LDV; i += blockDim.x) ring[i] = 1.0 + 1e-9 * i;
     if (tid == 0) {
         for (int s = 0; s < 8; ++s) { mbar_init(&full[s], 1); mbar_init(&empty[s], SHARED ? CW : 4); }
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     }
     __syncthreads();
-    const int total = GEMMS * NKC;
+    const int total = GEMMS * NKC;     // ring stages streamed
 
     if (warp >= CW) {
         // producers: warps 8,9 -> group 0 (or the shared ring), 10,11 -> group 1; alternate chunks
@@ -101,7 +103,7 @@ __global__ void __launch_bounds__((FLAGS & 256) ? 448 : 384, 1) kloop_kernel(con
         const int grp = SHARED ? 0 : (warp - CW) / 2, which = (warp - CW) % 2;
         if (SHARED && warp >= CW + 2) return;
         if (lane == 0) {
-            uint64_t* f = full + grp * 4; uint64_t* e = empty + grp * 4; double* r = ring + (size_t)grp * 4 * STAGE_BYTES / 8;
+            uint64_t* f = full + grp * DEPTH; uint64_t* e = empty + grp * DEPTH; double* r = ring + (size_t)grp * DEPTH * STAGE_BYTES / 8;
             for (int pos = which; pos < total; pos += 2) {
                 const int st = pos % DEPTH, round = pos / DEPTH;
                 mbar_wait(&e[st], (round & 1) ^ 1);
@@ -116,11 +118,11 @@ __global__ void __launch_bounds__((FLAGS & 256) ? 448 : 384, 1) kloop_kernel(con
     }
 
     const int group = warp / 4, wg = warp % 4, g = lane >> 2, t4 = lane & 3;
-    uint64_t* f = full + (SHARED ? 0 : group * 4);
-    uint64_t* e = empty + (SHARED ? 0 : group * 4);
-    const uint32_t ring_u = s32(ring) + (SHARED ? 0 : group * 4 * STAGE_BYTES) + (uint32_t)((wg * 40) * 4 + lane) * 8u;
+    uint64_t* f = full + (SHARED ? 0 : group * DEPTH);
+    uint64_t* e = empty + (SHARED ? 0 : group * DEPTH);
+    const uint32_t ring_u = s32(ring) + (SHARED ? 0 : group * DEPTH * STAGE_BYTES) + (uint32_t)((wg * 40) * 4 + lane) * 8u;
     const uint32_t v_u = s32(slot) + (uint32_t)((group * 16 + g) * LDV + t4) * 8u;
-    constexpr uint32_t NB1 = 8u * LDV * 8u, P1 = 160 * 32u;
+    constexpr uint32_t NB1 = 8u * LDV * 8u;
     double acc[5][2][2];
     for (int i = 0; i < 5; ++i) acc[i][0][0] = acc[i][0][1] = acc[i][1][0] = acc[i][1][1] = 0.0;
     double a0[5], a1[5], b00, b01, b10, b11;
@@ -144,27 +146,37 @@ __global__ void __launch_bounds__((FLAGS & 256) ? 448 : 384, 1) kloop_kernel(con
         b00 = lds64(v_u); b01 = lds64(v_u + NB1);
         #pragma unroll 1
         for (int ch = 0; ch < NKC; ++ch) {
-            const uint32_t sa = ring_u + st * STAGE_BYTES, vb = v_u + ch * 64;
-            #pragma unroll
-            for (int i = 0; i < 5; ++i) a1[i] = lds64(sa + P1 + i * 256u);
-            b10 = lds64(vb + 32u); b11 = lds64(vb + NB1 + 32u);
+            const uint32_t sa = ring_u + st * STAGE_BYTES, vb = v_u + ch * (P * 32);
             const int npos = pos + 1, nst = npos % DEPTH;
-            if ((FLAGS & F_XBLK) && (FLAGS & F_BAR)) {
-                const bool more = ch + 1 < NKC;
-                dmma_x10_then_wait(acc, a0, b00, b01, &f[more ? nst : st], ((more ? npos : pos) / DEPTH) & 1);
-            }
-            else {
-                #pragma unroll
-                for (int i = 0; i < 5; ++i) { dmma(acc[i][0][0], acc[i][0][1], a0[i], b00); dmma(acc[i][1][0], acc[i][1][1], a0[i], b01); }
-            }
-            if (ch + 1 < NKC) {
-                if ((FLAGS & F_BAR) && !(FLAGS & F_XBLK)) mbar_wait(&f[nst], (npos / DEPTH) & 1);
-                #pragma unroll
-                for (int i = 0; i < 5; ++i) a0[i] = lds64(ring_u + nst * STAGE_BYTES + i * 256u);
-                b00 = lds64(vb + 64u); b01 = lds64(vb + NB1 + 64u);
-            }
             #pragma unroll
-            for (int i = 0; i < 5; ++i) { dmma(acc[i][0][0], acc[i][0][1], a1[i], b10); dmma(acc[i][1][0], acc[i][1][1], a1[i], b11); }
+            for (int q = 0; q < P; q += 2) {
+                // panel q+1 of this stage
+                #pragma unroll
+                for (int i = 0; i < 5; ++i) a1[i] = lds64(sa + (q + 1) * PANEL_BYTES + i * 256u);
+                b10 = lds64(vb + (q + 1) * 32u); b11 = lds64(vb + NB1 + (q + 1) * 32u);
+                if ((FLAGS & F_XBLK) && (FLAGS & F_BAR) && q + 2 == P) {
+                    const bool more = ch + 1 < NKC;
+                    dmma_x10_then_wait(acc, a0, b00, b01, &f[more ? nst : st], ((more ? npos : pos) / DEPTH) & 1);
+                }
+                else {
+                    #pragma unroll
+                    for (int i = 0; i < 5; ++i) { dmma(acc[i][0][0], acc[i][0][1], a0[i], b00); dmma(acc[i][1][0], acc[i][1][1], a0[i], b01); }
+                }
+                // panel q+2: same stage, or panel 0 of the next stage
+                if (q + 2 < P) {
+                    #pragma unroll
+                    for (int i = 0; i < 5; ++i) a0[i] = lds64(sa + (q + 2) * PANEL_BYTES + i * 256u);
+                    b00 = lds64(vb + (q + 2) * 32u); b01 = lds64(vb + NB1 + (q + 2) * 32u);
+                }
+                else if (ch + 1 < NKC) {
+                    if ((FLAGS & F_BAR) && !(FLAGS & F_XBLK)) mbar_wait(&f[nst], (npos / DEPTH) & 1);
+                    #pragma unroll
+                    for (int i = 0; i < 5; ++i) a0[i] = lds64(ring_u + nst * STAGE_BYTES + i * 256u);
+                    b00 = lds64(vb + P * 32u); b01 = lds64(vb + NB1 + P * 32u);
+                }
+                #pragma unroll
+                for (int i = 0; i < 5; ++i) { dmma(acc[i][0][0], acc[i][0][1], a1[i], b10); dmma(acc[i][1][0], acc[i][1][1], a1[i], b11); }
+            }
             if (FLAGS & F_BAR) { __syncwarp(); if (lane == 0) mbar_arrive(&e[st]); }
             st = nst; pos = npos;
         }
@@ -215,28 +227,28 @@ __global__ void __launch_bounds__((FLAGS & 256) ? 448 : 384, 1) kloop_kernel(con
     if (sink == 12345.678) out[0] = sink;
 }
 
-template <int FLAGS>
+template <int FLAGS, int P = 2>
 double run(int sms, const double* mats, double* out)
 {
-    const size_t smem = 8 * STAGE_BYTES + 48 * LDV * 8 + 256;
+    const size_t smem = 80 * 1024 + 48 * LDV * 8 + 256;
     constexpr int NG = (FLAGS & F_G3) ? 3 : 2;
     const int threads = (NG * 4 + 4) * 32 > 448 ? 448 : (NG == 3 ? 448 : 384);
-    CK(cudaFuncSetAttribute(kloop_kernel<FLAGS>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    CK(cudaFuncSetAttribute(kloop_kernel<FLAGS, P>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     cudaEvent_t e0, e1;
     CK(cudaEventCreate(&e0)); CK(cudaEventCreate(&e1));
-    kloop_kernel<FLAGS><<<sms, threads, smem>>>(mats, out);
+    kloop_kernel<FLAGS, P><<<sms, threads, smem>>>(mats, out);
     CK(cudaGetLastError());
     CK(cudaDeviceSynchronize());
     double best = 1e30;
     for (int r = 0; r < 3; ++r) {
         CK(cudaEventRecord(e0));
-        kloop_kernel<FLAGS><<<sms, threads, smem>>>(mats, out);
+        kloop_kernel<FLAGS, P><<<sms, threads, smem>>>(mats, out);
         CK(cudaEventRecord(e1));
         CK(cudaEventSynchronize(e1));
         float ms; CK(cudaEventElapsedTime(&ms, e0, e1));
         best = std::min(best, (double)ms);
     }
-    const double flops = 2.0 * 8 * 8 * 4 * 20.0 * NKC * GEMMS * (double)sms * (NG * 4);
+    const double flops = 2.0 * 8 * 8 * 4 * 10.0 * NPANELS * GEMMS * (double)sms * (NG * 4);
     return flops / best / 1e9;
 }
 
@@ -246,7 +258,7 @@ int main()
     CK(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, 0));
     double *out, *mats;
     CK(cudaMalloc(&out, 64));
-    const size_t mat_bytes = std::max((size_t)2048 * STAGE_BYTES, (size_t)198 * 151 * 160 * 8);
+    const size_t mat_bytes = std::max((size_t)2048 * 20480, (size_t)198 * 151 * 160 * 8);
     CK(cudaMalloc(&mats, mat_bytes));
     CK(cudaMemset(mats, 0, mat_bytes));
     printf("{\"sms\": %d", sms);
@@ -269,6 +281,10 @@ int main()
     printf(", \"g3_bar_copy_gemm\": %.2f", run<F_G3 | F_SHARED | F_BAR | F_COPY | F_GEMM>(sms, mats, out));
     printf(", \"g3_all\": %.2f", run<F_G3 | F_SHARED | F_BAR | F_COPY | F_GEMM | F_DMUL | F_LEAF>(sms, mats, out));
     printf(", \"g3_all_pref\": %.2f", run<F_G3 | F_SHARED | F_BAR | F_COPY | F_GEMM | F_DMUL | F_LEAF | F_PREF>(sms, mats, out));
+    printf(", \"shared_bar_copy_P4\": %.2f", run<F_SHARED | F_BAR | F_COPY, 4>(sms, mats, out));
+    printf(", \"shared_all_P4\": %.2f", run<F_SHARED | F_BAR | F_COPY | F_GEMM | F_DMUL | F_LEAF, 4>(sms, mats, out));
+    printf(", \"shared_all_pref_P4\": %.2f", run<F_SHARED | F_BAR | F_COPY | F_GEMM | F_DMUL | F_LEAF | F_PREF, 4>(sms, mats, out));
+    printf(", \"g3_all_pref_P4\": %.2f", run<F_G3 | F_SHARED | F_BAR | F_COPY | F_GEMM | F_DMUL | F_LEAF | F_PREF, 4>(sms, mats, out));
     printf(", \"shared_bar\": %.2f", run<F_SHARED | F_BAR>(sms, mats, out));
     printf(", \"shared_bar_copy\": %.2f", run<F_SHARED | F_BAR | F_COPY>(sms, mats, out));
     printf(", \"shared_bar_copy_gemm\": %.2f", run<F_SHARED | F_BAR | F_COPY | F_GEMM>(sms, mats, out));
