@@ -490,7 +490,8 @@ int launch_prune(cafe_b200_ctx* c, int k, int mode, double* root_out)
     p.rescale = c->rescale; p.n_spill = std::max(1, c->psched.n_spill); p.err_rows = c->err_rows; p.err_ndev = c->err_ndev;
     p.counts_in_smem = (pft * c->n_leaves * 2 <= PRUNE_CNT_CAP_BYTES) ? 1 : 0;
     p.n_slots = c->prune_slots; p.n_tiles = (c->n_families + pft - 1) / pft;
-    p.n_stages = c->n_stages; p.stage_shift = c->n_stages == 8 ? 3 : (c->n_stages == 4 ? 2 : 1);
+    // c->n_stages counts 10 KB chunks of ring memory; the kernel's stages hold CPS chunks each
+    p.n_stages = c->n_stages / CPS; p.stage_shift = p.n_stages == 4 ? 2 : (p.n_stages == 2 ? 1 : 0);
     // consecutive groups start a few ring stages apart: half the ring depth in chunk times, a chunk being
     // 2*PPS*MB DMMAs of 16 cycles for each of the n_groups warps on a sub-partition
     p.stagger_cycles = (c->n_stages / 2) * (2 * PPS * c->mb * 16 * c->n_groups) / (c->n_groups - 1);

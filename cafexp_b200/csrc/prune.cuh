@@ -22,7 +22,7 @@
 // [16g, 16g+16) of the tile (its rows of every slot), has its own named barrier and walks the same op list at its
 // own pace; both groups consume the SAME matrix stream from the shared ring (a stage is released when every consumer
 // warp has read it), so the L2 traffic per flop is that of a 32-family tile and the groups can drift up to one ring
-// depth (8 chunks) apart: while one group is between GEMMs (epilogue, child product, leaf gathers at L2 latency,
+// depth (4 stages of 2 chunks) apart: while one group is between GEMMs (epilogue, child product, leaf gathers at L2 latency,
 // barriers) the other keeps the FP64 pipe busy.  Inside a GEMM the A/B fragments are double-buffered in registers
 // across ring stages; the leaf-sibling factors of the epilogue are gathered after the K loop, when the fragment
 // registers are free.  NG = 3 (48-family tiles, two slots) is compiled for experiments, see plan_shared_memory.
@@ -47,6 +47,7 @@ constexpr int GFT = 16;                                  // families per group =
 constexpr int FPW = GFT / GROUP_WARPS;                   // 4 families per warp in the gather / root ops
 constexpr int PRODUCER_WARPS = 2;                        // take alternate chunks of the one matrix stream
 constexpr int MAX_GROUPS = 3;
+constexpr int CPS = 2;                                   // K chunks (of PPS panels) per ring stage: one mbarrier pair per 40 DMMAs
 constexpr int PRUNE_CNT_CAP_BYTES = 12288;               // staged leaf counts (uint16) of a 48-family tile, if they fit
 __host__ __device__ constexpr int prune_threads(int ng) { return (ng * GROUP_WARPS + PRODUCER_WARPS) * 32; }
 
@@ -55,17 +56,19 @@ struct PruneSmem {
     static constexpr int PFT = NG * GFT;                 // families per thread-block tile
     static constexpr int NR = nr_of(MB);
     static constexpr int LDV = ldv_of(MB);
-    static constexpr int STAGE_DOUBLES = stage_doubles(MB);
+    static constexpr int CHUNK_DOUBLES = stage_doubles(MB);          // PPS panels = 8 matrix columns
+    static constexpr int CHUNK_BYTES = CHUNK_DOUBLES * 8;
+    static constexpr int STAGE_DOUBLES = CPS * CHUNK_DOUBLES;        // a ring stage = CPS chunks (contiguous in the panelised matrix)
     static constexpr int STAGE_BYTES = STAGE_DOUBLES * 8;
     static constexpr int SLOT_DOUBLES = PFT * LDV;
     static constexpr int SLOT_BYTES = SLOT_DOUBLES * 8;
     static constexpr int MISC_BYTES = 512;     // mbarriers
     static constexpr int EXP_BYTES = MAX_SLOTS * PFT * 4;
-    __host__ __device__ static constexpr int ring_bytes(int stages) { return stages * STAGE_BYTES; }
-    __host__ __device__ static constexpr int total_bytes(int slots, int stages) { return ring_bytes(stages) + slots * SLOT_BYTES + PRUNE_CNT_CAP_BYTES + MISC_BYTES + EXP_BYTES; }
-    __host__ static int max_slots(int smem_limit, int stages)
+    __host__ __device__ static constexpr int ring_bytes(int chunks) { return chunks * CHUNK_BYTES; }        // ring memory is sized in chunks
+    __host__ __device__ static constexpr int total_bytes(int slots, int chunks) { return ring_bytes(chunks) + slots * SLOT_BYTES + PRUNE_CNT_CAP_BYTES + MISC_BYTES + EXP_BYTES; }
+    __host__ static int max_slots(int smem_limit, int chunks)
     {
-        int s = (smem_limit - ring_bytes(stages) - PRUNE_CNT_CAP_BYTES - MISC_BYTES - EXP_BYTES) / SLOT_BYTES;
+        int s = (smem_limit - ring_bytes(chunks) - PRUNE_CNT_CAP_BYTES - MISC_BYTES - EXP_BYTES) / SLOT_BYTES;
         return s > MAX_SLOTS ? MAX_SLOTS : s;
     }
 };
@@ -85,7 +88,7 @@ __global__ void __launch_bounds__(prune_threads(NG), 1) prune_kernel(const Prune
     constexpr int LDV = L::LDV;
     extern __shared__ __align__(128) unsigned char smem_raw[];
     double* ring = reinterpret_cast<double*>(smem_raw);
-    const int ring_bytes = L::ring_bytes(p.n_stages);
+    const int ring_bytes = L::ring_bytes(p.n_stages * CPS);
     const uint32_t stage_mask = (uint32_t)p.n_stages - 1u;
     double* slots = reinterpret_cast<double*>(smem_raw + ring_bytes);
     uint16_t* cnt_s = reinterpret_cast<uint16_t*>(smem_raw + ring_bytes + p.n_slots * L::SLOT_BYTES);
@@ -120,13 +123,14 @@ __global__ void __launch_bounds__(prune_threads(NG), 1) prune_kernel(const Prune
                     const int type = ops[o].type;
                     if (type != OP_GEMM_SET && type != OP_GEMM_MUL && type != OP_GEMM_SET_LEAF && type != OP_GEMM_MUL_LEAF) continue;
                     const double* src = p.mp + (size_t)ops[o].mat * p.mp_stride;
-                    for (int ch = 0; ch < p.n_kchunks; ++ch, ++pos) {
+                    for (int ch = 0; ch < p.n_kchunks; ch += CPS, ++pos) {
                         if ((int)(pos % PRODUCER_WARPS) != which) continue;
                         const uint32_t stage = pos & stage_mask;
                         const uint32_t round = pos >> p.stage_shift;
+                        const uint32_t bytes = (uint32_t)min(CPS, p.n_kchunks - ch) * L::CHUNK_BYTES;      // the last stage of a GEMM may be partial
                         mbar_wait(&empty_bar[stage], (round & 1) ^ 1);
-                        mbar_arrive_expect_tx(&full_bar[stage], L::STAGE_BYTES);
-                        bulk_copy_g2s(ring + (size_t)stage * L::STAGE_DOUBLES, src + (size_t)ch * L::STAGE_DOUBLES, L::STAGE_BYTES, &full_bar[stage]);
+                        mbar_arrive_expect_tx(&full_bar[stage], bytes);
+                        bulk_copy_g2s(ring + (size_t)stage * L::STAGE_DOUBLES, src + (size_t)ch * L::CHUNK_DOUBLES, bytes, &full_bar[stage]);
                     }
                 }
             }
@@ -275,6 +279,7 @@ __global__ void __launch_bounds__(prune_threads(NG), 1) prune_kernel(const Prune
                 for (int i = 0; i < MB; ++i) acc[i][0][0] = acc[i][0][1] = acc[i][1][0] = acc[i][1][1] = 0.0;
                 // Fragments are double-buffered in registers: the loads of panel q+1 (possibly from the next
                 // ring stage) are issued before the MMAs of panel q, so shared-memory latency never gates the pipe.
+                // A ring stage holds CPS chunks: the full / empty mbarriers are touched once per CPS * 20 DMMAs.
                 const int a_off = (wg * 8 * MB) * 4 + lane;
                 double a0[MB], a1[MB], b00, b01, b10, b11;
                 uint32_t stage = pos & stage_mask;
@@ -288,11 +293,13 @@ __global__ void __launch_bounds__(prune_threads(NG), 1) prune_kernel(const Prune
                 }
                 #pragma unroll 1
                 for (int ch = 0; ch < p.n_kchunks; ++ch) {
-                    const double* a_stage = ring + (size_t)stage * L::STAGE_DOUBLES + a_off;
+                    const int sub = ch & (CPS - 1);                                     // chunk inside the stage
+                    const double* a_chunk = ring + (size_t)stage * L::STAGE_DOUBLES + (size_t)sub * L::CHUNK_DOUBLES + a_off;
                     const int kcol = ch * (PPS * 4);
-                    // panel 1 of this stage
+                    const bool last_of_stage = (sub == CPS - 1) || (ch + 1 == p.n_kchunks);
+                    // panel 1 of this chunk
                     #pragma unroll
-                    for (int i = 0; i < MB; ++i) a1[i] = a_stage[NR * 4 + i * 32];
+                    for (int i = 0; i < MB; ++i) a1[i] = a_chunk[NR * 4 + i * 32];
                     b10 = vsrc[kcol + 4];
                     b11 = vsrc[8 * LDV + kcol + 4];
                     #pragma unroll
@@ -300,14 +307,14 @@ __global__ void __launch_bounds__(prune_threads(NG), 1) prune_kernel(const Prune
                         dmma_m8n8k4(acc[i][0][0], acc[i][0][1], a0[i], b00);
                         dmma_m8n8k4(acc[i][1][0], acc[i][1][1], a0[i], b01);
                     }
-                    // panel 0 of the next stage
-                    const uint32_t npos = pos + 1;
+                    // panel 0 of the next chunk: same stage, or the next one (wait for it first)
+                    const uint32_t npos = pos + (last_of_stage ? 1u : 0u);
                     const uint32_t nstage = npos & stage_mask;
                     if (ch + 1 < p.n_kchunks) {
-                        mbar_wait(&full_bar[nstage], (npos >> p.stage_shift) & 1);
-                        const double* n_stage = ring + (size_t)nstage * L::STAGE_DOUBLES + a_off;
+                        if (last_of_stage) mbar_wait(&full_bar[nstage], (npos >> p.stage_shift) & 1);
+                        const double* n_chunk = last_of_stage ? ring + (size_t)nstage * L::STAGE_DOUBLES + a_off : a_chunk + L::CHUNK_DOUBLES;
                         #pragma unroll
-                        for (int i = 0; i < MB; ++i) a0[i] = n_stage[i * 32];
+                        for (int i = 0; i < MB; ++i) a0[i] = n_chunk[i * 32];
                         b00 = vsrc[kcol + 8];
                         b01 = vsrc[8 * LDV + kcol + 8];
                     }
@@ -316,9 +323,11 @@ __global__ void __launch_bounds__(prune_threads(NG), 1) prune_kernel(const Prune
                         dmma_m8n8k4(acc[i][0][0], acc[i][0][1], a1[i], b10);
                         dmma_m8n8k4(acc[i][1][0], acc[i][1][1], a1[i], b11);
                     }
-                    // every load of this stage has been consumed by an MMA above
-                    __syncwarp();
-                    if (lane == 0) mbar_arrive(&empty_bar[stage]);
+                    if (last_of_stage) {
+                        // every load of this stage has been consumed by an MMA above
+                        __syncwarp();
+                        if (lane == 0) mbar_arrive(&empty_bar[stage]);
+                    }
                     stage = nstage;
                     pos = npos;
                 }
