@@ -308,3 +308,23 @@ def test_set_families_and_launch_accounting(mammal):
         assert np.array_equal(b["family_lnl"], a["family_lnl"][::-1])
         t = eng.last_timings_ms()
         assert t["prune"] > 0 and t["matrix_build"] > 0
+
+
+def test_three_group_layout_matches_two_group_results(mammal, monkeypatch):
+    """The experimental 48-family tile layout (CAFE_B200_GROUPS=3: three consumer groups, two vector slots, more spills)
+    computes the same numbers as the shipped one: same MMA tiles and the same order of every product."""
+    flat, counts = mammal["tree"], mammal["counts"][:1500]
+    mf, mrf = mammal["mf"], mammal["mrf"]
+    freq, rate = orc.get_gamma(3, 0.6)
+    lams = rate[:, None] * np.array([[0.0025]])
+    prior = orc.prior_uniform(mrf)
+    with engine.Engine(flat, counts, mf, mrf) as eng:
+        two = eng.infer(lams, prior, freq, engine.GAMMA_LINSUM)
+        roots2 = eng.prune_roots(lams[:1])
+    monkeypatch.setenv("CAFE_B200_GROUPS", "3")
+    with engine.Engine(flat, counts, mf, mrf) as eng:
+        three = eng.infer(lams, prior, freq, engine.GAMMA_LINSUM)
+        roots3 = eng.prune_roots(lams[:1])
+    assert np.array_equal(two["cat_lk"], three["cat_lk"], equal_nan=True)
+    assert np.array_equal(roots2, roots3)
+    assert two["score"] == three["score"] and two["n_failed"] == three["n_failed"]
