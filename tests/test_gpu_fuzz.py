@@ -39,26 +39,27 @@ def random_newick(rng, n_leaves, shape, max_children):
     return nodes[0] + ";"
 
 
-def make_case(seed):
+def make_case(seed, big=False):
     rng = np.random.default_rng(seed)
-    n_leaves = int(rng.choice([2, 3, 5, 8, 13, 24, 40]))
+    n_leaves = int(rng.choice([250, 400])) if big else int(rng.choice([2, 3, 5, 8, 13, 24, 40]))
     shape = str(rng.choice(["random", "caterpillar"]))
     max_children = int(rng.choice([2, 2, 3, 4]))
     flat = hostio.flatten_tree(hostio.parse_newick(random_newick(rng, n_leaves, shape, max_children)))
-    mf = int(rng.choice([5, 20, 31, 32, 63, 64, 100, 127, 159, 160, 200, 249]))
+    mf = int(rng.choice([12, 31, 40])) if big else int(rng.choice([5, 20, 31, 32, 63, 64, 100, 127, 159, 160, 200, 249]))
     mrf = int(np.clip(mf + rng.integers(-mf // 2, 6), 1, 249))
     n_lambdas = int(rng.choice([1, 1, 2, 3]))
     flat.lambda_index[:] = rng.integers(0, n_lambdas, size=flat.n_nodes)
-    F = int(rng.choice([1, 7, 16, 33, 100, 257]))
+    F = int(rng.choice([5, 33, 70])) if big else int(rng.choice([1, 7, 16, 33, 100, 257]))
     ndev = int(rng.choice([0, 0, 3, 5]))
     hi = max(1, mf - (ndev - 1) // 2 - 1 if ndev else mf)
-    counts = np.minimum(rng.poisson(rng.uniform(0.5, min(30, hi)), size=(F, flat.n_leaves)), hi).astype(np.int32)
+    mean_hi = 2.0 if big else min(30, hi)          # many leaves: keep the likelihood inside the double range
+    counts = np.minimum(rng.poisson(rng.uniform(0.5, mean_hi), size=(F, flat.n_leaves)), hi).astype(np.int32)
     if rng.random() < 0.3:
         counts[rng.integers(0, F)] = 0                                    # an all-zero family
     if rng.random() < 0.3:
         counts[rng.integers(0, F)] = hi                                   # the largest allowed counts
     k = int(rng.choice([1, 1, 2, 4, 7]))
-    lam = rng.uniform(0.0005, 0.03, size=n_lambdas)
+    lam = rng.uniform(0.0005, 0.004 if big else 0.03, size=n_lambdas)
     if k > 1:
         freq, rate = orc.get_gamma(k, float(rng.uniform(0.2, 2.0)))
     else:
@@ -74,9 +75,19 @@ def make_case(seed):
                 slots=int(rng.choice([0, 0, 2, 3])), rescale=bool(rng.random() < 0.3), n_leaves=n_leaves, shape=shape)
 
 
+@pytest.mark.parametrize("seed", range(1000, 1006))
+def test_random_big_tree_against_oracle(seed):
+    """250 / 400 leaves: the per-tile counts no longer fit the shared-memory staging area (counts read from global
+    memory), the op list has thousands of entries, the schedule spills."""
+    check_case(make_case(seed, big=True))
+
+
 @pytest.mark.parametrize("seed", range(int(os.environ.get("CAFE_B200_FUZZ_SEEDS", "40"))))
 def test_random_case_against_oracle(seed):
-    c = make_case(seed)
+    check_case(make_case(seed))
+
+
+def check_case(c):
     flat, mf, mrf, counts, k, lams = c["flat"], c["mf"], c["mrf"], c["counts"], c["k"], c["lams"]
     prior = orc.prior_uniform(mrf, None, max(mf, mrf) + 1)
     mode = orc.GAMMA_LINSUM if k > 1 else orc.BASE_LOGMAX
