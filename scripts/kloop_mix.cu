@@ -285,6 +285,8 @@ int main()
     printf(", \"shared_all_P4\": %.2f", run<F_SHARED | F_BAR | F_COPY | F_GEMM | F_DMUL | F_LEAF, 4>(sms, mats, out));
     printf(", \"shared_all_pref_P4\": %.2f", run<F_SHARED | F_BAR | F_COPY | F_GEMM | F_DMUL | F_LEAF | F_PREF, 4>(sms, mats, out));
     printf(", \"g3_all_pref_P4\": %.2f", run<F_G3 | F_SHARED | F_BAR | F_COPY | F_GEMM | F_DMUL | F_LEAF | F_PREF, 4>(sms, mats, out));
+    printf(", \"shared_gemm_dmul\": %.2f", run<F_SHARED | F_BAR | F_COPY | F_GEMM | F_DMUL>(sms, mats, out));
+    printf(", \"shared_gemm_dmul_P4\": %.2f", run<F_SHARED | F_BAR | F_COPY | F_GEMM | F_DMUL, 4>(sms, mats, out));
     printf(", \"shared_bar\": %.2f", run<F_SHARED | F_BAR>(sms, mats, out));
     printf(", \"shared_bar_copy\": %.2f", run<F_SHARED | F_BAR | F_COPY>(sms, mats, out));
     printf(", \"shared_bar_copy_gemm\": %.2f", run<F_SHARED | F_BAR | F_COPY | F_GEMM>(sms, mats, out));
