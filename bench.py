@@ -104,12 +104,12 @@ class ClockSampler:
 
 
 def gamma_parameters():
-    """Discrete-gamma multipliers and category probabilities.  Host-side scalar math of the reference
-    (get_gamma, src/gamma.cpp:225); taken from the checker library because the host mirror in C++ is not
-    part of the timed path."""
-    from oracle import binding as orc
-    freq, rate = orc.get_gamma(K, ALPHA)
-    prior = orc.prior_uniform(MRF, None, MRF)
+    """Discrete-gamma multipliers, category probabilities and the uniform root prior: host-side scalar math of the
+    reference (get_gamma, src/gamma.cpp:225; uniform_distribution, src/root_equilibrium_distribution.cpp:20-32),
+    from the product's own host mirror."""
+    from cafexp_b200 import params
+    freq, rate = params.get_gamma(K, ALPHA)
+    prior = params.prior_uniform(MRF, None, MRF)
     return freq, rate, prior
 
 

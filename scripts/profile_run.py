@@ -30,8 +30,8 @@ def main():
             res = eng.infer(lams, prior, freq, engine.GAMMA_LINSUM, want_family=False, want_cat=False)
         print("score", res["score"], eng.last_timings_ms())
     if args.recon:
-        from oracle import binding as orc
-        prior_sz = orc.prior_uniform(bench.MRF, None, min(bench.MF, bench.MRF) + 1)
+        from cafexp_b200 import params
+        prior_sz = params.prior_uniform(bench.MRF, None, min(bench.MF, bench.MRF) + 1)
         with engine.Engine(tree, counts[: args.recon], bench.MF, bench.MRF) as eng:
             eng.reconstruct(lams, prior_sz)
             print("reconstruct", eng.last_timings_ms())

@@ -159,3 +159,23 @@ def test_mammal_host_preparation(mammal):
     names = mammal["tree2"].names
     lam_idx = dict(zip(names, mammal["tree2"].lambda_index))
     assert lam_idx["chimp"] == 1 and lam_idx["human"] == 1 and lam_idx["chimphuman"] == 1 and lam_idx["orang"] == 0
+
+
+def test_host_parameter_mirror_matches_reference_and_oracle():
+    """cafexp_b200/params.py (discrete gamma, root priors — what a Python host feeds the C ABI) against the compiled
+    reference's values (tests/golden/scalars.json) and, bit for bit, against the oracle."""
+    import json
+    from cafexp_b200 import params
+    gold = json.load(open(os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden", "scalars.json")))
+    for case in gold["gamma"]:
+        freq, rate = params.get_gamma(case["k"], case["alpha"])
+        assert np.allclose(rate, case["rate"], rtol=1e-13, atol=0) and np.allclose(freq, case["freq"], rtol=1e-15, atol=0), case
+        f2, r2 = orc.get_gamma(case["k"], case["alpha"])
+        assert np.array_equal(rate, r2) and np.array_equal(freq, f2)
+    for case in gold["poisson"]:
+        got = params.prior_poisson(case["lambda"], case["n"], None, case["n"] + 2)
+        assert np.allclose(got, case["prior"], rtol=1e-15, atol=0), case
+    rd = {1: 5, 2: 3, 7: 1}
+    assert np.array_equal(params.prior_uniform(30), orc.prior_uniform(30))
+    assert np.array_equal(params.prior_uniform(30, rd, 40), orc.prior_uniform(30, rd, 40))
+    assert np.array_equal(params.prior_poisson(2.5, 30, rd, 35), orc.prior_poisson(2.5, 30, rd, 35))
