@@ -492,10 +492,6 @@ int launch_prune(cafe_b200_ctx* c, int k, int mode, double* root_out)
     p.n_slots = c->prune_slots; p.n_tiles = (c->n_families + pft - 1) / pft;
     // c->n_stages counts 10 KB chunks of ring memory; the kernel's stages hold CPS chunks each
     p.n_stages = c->n_stages / CPS; p.stage_shift = p.n_stages == 4 ? 2 : (p.n_stages == 2 ? 1 : 0);
-    // consecutive groups start a few ring stages apart: half the ring depth in chunk times, a chunk being
-    // 2*PPS*MB DMMAs of 16 cycles for each of the n_groups warps on a sub-partition
-    p.stagger_cycles = (c->n_stages / 2) * (2 * PPS * c->mb * 16 * c->n_groups) / (c->n_groups - 1);
-    if (const char* e = getenv("CAFE_B200_STAGGER")) p.stagger_cycles = atoi(e);
     p.ops = c->d_pops; p.counts = c->d_counts;
     p.mp = c->d_mp; p.mt = c->d_mt; p.mp_stride = c->mp_stride; p.mt_stride = c->mt_stride;
     p.err = c->d_err; p.prior = c->d_prior; p.logprior = c->d_logprior; p.cat_probs = c->d_catprobs;

@@ -82,7 +82,6 @@ struct PruneParams {
     int n_slots;
     int n_stages;           // ring depth (power of two)
     int stage_shift;        // log2(n_stages)
-    int stagger_cycles;     // one-time start delay between consecutive consumer groups (SM cycles)
     int64_t n_tiles;        // tiles of (groups x 16) families = work items per category
     // device pointers
     const POp* ops;                 // [k][n_ops]

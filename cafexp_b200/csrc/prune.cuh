@@ -148,13 +148,6 @@ __global__ void __launch_bounds__(prune_threads(NG), 1) prune_kernel(const Prune
     uint32_t pos = 0;
     uint16_t* my_cnt = cnt_s + (size_t)fbase * p.n_leaves;
 
-    // One-time stagger: the groups run the same op list at the same speed, so the phase difference they start with
-    // persists (up to the ring depth); started together they would all sit between two GEMMs at the same time.
-    if (group > 0 && p.stagger_cycles > 0) {
-        const long long t0 = clock64(), d = (long long)group * p.stagger_cycles;
-        while (clock64() - t0 < d) { }
-    }
-
     for (int64_t item = blockIdx.x; item < n_items; item += gridDim.x) {
         const int cat = (int)(item / p.n_tiles);
         const int64_t tile = item % p.n_tiles;
