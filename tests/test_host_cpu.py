@@ -179,3 +179,21 @@ def test_host_parameter_mirror_matches_reference_and_oracle():
     assert np.array_equal(params.prior_uniform(30), orc.prior_uniform(30))
     assert np.array_equal(params.prior_uniform(30, rd, 40), orc.prior_uniform(30, rd, 40))
     assert np.array_equal(params.prior_poisson(2.5, 30, rd, 35), orc.prior_poisson(2.5, 30, rd, 35))
+
+
+def test_header_is_plain_c(tmp_path):
+    """include/cafe_b200.h is the drop-in boundary: it must compile as C99 (no C++, no torch / CUDA types)."""
+    import shutil
+    import subprocess
+    gcc = shutil.which("gcc") or "/usr/bin/gcc"
+    src = tmp_path / "abi.c"
+    src.write_text('#include "cafe_b200.h"\nint main(void) { cafe_b200_limits l; cafe_b200_get_limits(&l); return cafe_b200_abi_version() + l.max_categories; }\n')
+    res = subprocess.run([gcc, "-std=c99", "-pedantic", "-Wall", "-Werror", "-fsyntax-only", "-I", os.path.join(ROOT, "include"), str(src)],
+                         capture_output=True, text=True)
+    assert res.returncode == 0, res.stderr
+    # and link-runs against the built library
+    exe = tmp_path / "abi"
+    res = subprocess.run([gcc, "-std=c99", "-I", os.path.join(ROOT, "include"), str(src), "-o", str(exe), "-L", os.path.join(ROOT, "cafexp_b200"),
+                          "-lcafe_b200", "-Wl,-rpath," + os.path.join(ROOT, "cafexp_b200")], capture_output=True, text=True)
+    assert res.returncode == 0, res.stderr
+    assert subprocess.run([str(exe)]).returncode > 0
