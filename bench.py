@@ -195,7 +195,7 @@ def workload_config(args, world):
 
 def measure_fp64_peak():
     """FP64 DMMA / cuBLAS DGEMM peak on this box (scripts/fp64_peak.cu); falls back to the committed measurement."""
-    exe = os.path.join(ROOT, "scripts", "fp64_peak.bin.so")
+    exe = os.path.join(ROOT, "scripts", "bin", "fp64_peak")
     try:
         out = subprocess.run([exe], check=True, capture_output=True, text=True, timeout=120).stdout
         d = json.loads(out.strip().splitlines()[-1])

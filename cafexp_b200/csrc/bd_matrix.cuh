@@ -8,8 +8,8 @@
 //
 // P(s -> c) = clamp01( sum_{j=0}^{min(s,c)} exp(t_j) * coeff^j ),
 //   t_j = lnC(s, j) + lnC(s+c-1-j, s-1) + (s+c-2j) * ln(alpha)
-// The reference evaluates t_j from a 1024-entry table of libm lgamma values; the host uploads ITS
-// table, ln(alpha), coeff and the pow(coeff, j) row, so every input of exp() is bit-identical to
+// The reference evaluates t_j from a 1024-entry table of libm lgamma values (libm itself beyond it,
+// src/probability.cpp:58-64); the host uploads those values for every argument up to 2 N, ln(alpha), coeff and the pow(coeff, j) row, so every input of exp() is bit-identical to
 // the reference's and the terms are added in the same ascending-j order without FMA contraction.
 // Only exp() itself (CUDA libdevice vs glibc, both < 1 ulp) can differ.
 //
@@ -39,9 +39,10 @@ struct MatrixBuildParams {
     int mf;            // columns kept: c <= mf
     int nr;            // padded rows
     int n_keys;
+    int lg_len;        // entries of the lgamma table (2 N + 2)
     const KeyParams* keys;      // [n_keys]
     const double* powc;         // [n_keys][n]  pow(coeff, j) from the host libm
-    const double* lgamma_tab;   // [1024]       lgamma(i) from the host libm
+    const double* lgamma_tab;   // [lg_len]     lgamma(i) from the host libm
     double* mp;
     double* mt;
     size_t mp_stride;
@@ -56,11 +57,11 @@ constexpr int MB_THREADS = 256;
 __global__ void __launch_bounds__(MB_THREADS) bd_matrix_kernel(const MatrixBuildParams p)
 {
     extern __shared__ double sm[];
-    double* lg = sm;                       // [1024]
-    double* pw = sm + LGAMMA_TABLE;        // [n]
+    double* lg = sm;                       // [lg_len]
+    double* pw = sm + p.lg_len;            // [n]
     const int key = blockIdx.y;
     const KeyParams kp = p.keys[key];
-    for (int i = threadIdx.x; i < LGAMMA_TABLE; i += MB_THREADS) lg[i] = p.lgamma_tab[i];
+    for (int i = threadIdx.x; i < p.lg_len; i += MB_THREADS) lg[i] = p.lgamma_tab[i];
     for (int i = threadIdx.x; i < p.n; i += MB_THREADS) pw[i] = p.powc[(size_t)key * p.n + i];
     __syncthreads();
 

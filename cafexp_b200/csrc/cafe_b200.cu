@@ -3,23 +3,37 @@
 // Host work per evaluation is what the reference also does on the host before its hot loops:
 // quantise (lambda, t) into matrix_cache keys (src/matrix_cache.h:47-60), derive alpha / coeff /
 // log(alpha) (src/probability.cpp:150-156) — here once per unique key instead of once per matrix
-// entry — and hand the device a flat schedule of the tree.  Everything O(families) or O(N^2) runs
+// entry — and hand the device a flat program of the tree.  Everything O(families) or O(N^2) runs
 // on the GPU.  There is no CPU fallback.
+//
+// A context owns one SHARD per CUDA device it was created on (contiguous family ranges): every
+// entry point stages its host inputs once, enqueues the work on every shard's stream without waiting, then
+// synchronises and combines — the score as the sum of the shards' [sum lnL, #failed] pairs in shard order on
+// the host (N pinned pairs: deterministic, no collective library inside the drop-in, 16 bytes per device).
+//
+// Evaluation state is persistent: buffers, pinned staging, kernel attributes and the
+// error-model table are set up once; an evaluation is one packed host->device copy, four kernel launches and one
+// small device->host copy per shard, with no allocation and no synchronisation besides the final one.
 #include "../../include/cafe_b200.h"
 
 #include <algorithm>
 #include <climits>
 #include <cmath>
 #include <cstdio>
+#include <cstdlib>
 #include <cstring>
 #include <map>
 #include <string>
 #include <utility>
 #include <vector>
 
+#include <nvtx3/nvToolsExt.h>
+
 #include "bd_matrix.cuh"
 #include "common.cuh"
+#include "plan.h"
 #include "prune.cuh"
+#include "prune_launch.h"
 #include "pupko.cuh"
 #include "pvalue.cuh"
 #include "reduce.cuh"
@@ -31,214 +45,10 @@ namespace {
 
 std::string g_create_error;
 
-struct Schedule {
-    std::vector<Op> ops;
-    int n_spill = 0;
+struct NvtxRange {
+    explicit NvtxRange(const char* name) { nvtxRangePushA(name); }
+    ~NvtxRange() { nvtxRangePop(); }
 };
-
-struct FusedOp {
-    int type, a, b, node, node2;
-};
-
-struct HostTree {
-    int n_nodes = 0;
-    std::vector<int> parent, child_offset, child_list, leaf_col, lambda_index;
-    std::vector<double> branch;
-    std::vector<long> branch_key;       // long(t * 1000)                         src/matrix_cache.h:50
-    int n_internal = 0;
-    int n_lambdas = 1;
-    bool is_leaf(int v) const { return child_offset[v] == child_offset[v + 1]; }
-};
-
-// Post-order schedule with Sethi-Ullman ordering of internal children, so that the number of
-// partial-likelihood vectors alive at once is the tree's Strahler-like "need"; vectors beyond the
-// shared-memory slots are spilled to an L2-resident scratch area (rare: need <= log2(leaves)+1).
-class ScheduleBuilder {
-public:
-    ScheduleBuilder(const HostTree& t, int slots) : tree(t), n_slots(slots), owner(slots, -1) { compute_need(); }
-
-    Schedule build()
-    {
-        int root = tree.n_nodes - 1;
-        int vid = emit(root);
-        make_resident(vid, -1);
-        out.ops.push_back({OP_ROOT, where[vid], 0, root});
-        return out;
-    }
-
-private:
-    const HostTree& tree;
-    int n_slots;
-    std::vector<int> owner;                 // physical slot -> vector id
-    std::vector<int> where;                 // vector id -> slot (>= 0) or -(spill index + 1)
-    std::vector<int> birth;                 // vector id -> creation order (victim choice: oldest)
-    std::vector<int> free_spill;
-    std::vector<int> need;
-    Schedule out;
-    int clock = 0;
-
-    void compute_need()
-    {
-        need.assign(tree.n_nodes, 0);
-        for (int v = 0; v < tree.n_nodes; ++v) {
-            if (tree.is_leaf(v)) continue;
-            std::vector<int> ns;
-            for (int e = tree.child_offset[v]; e < tree.child_offset[v + 1]; ++e) {
-                int c = tree.child_list[e];
-                if (!tree.is_leaf(c)) ns.push_back(need[c]);
-            }
-            std::sort(ns.rbegin(), ns.rend());
-            int n = 1;
-            for (size_t i = 0; i < ns.size(); ++i) n = std::max(n, ns[i] + (i > 0 ? 1 : 0));
-            need[v] = n;
-        }
-    }
-
-    int new_vector()
-    {
-        where.push_back(-1000000);
-        birth.push_back(clock++);
-        return (int)where.size() - 1;
-    }
-
-    int acquire(int pin_a, int pin_b)
-    {
-        for (int s = 0; s < n_slots; ++s)
-            if (owner[s] < 0) return s;
-        int victim = -1;
-        for (int s = 0; s < n_slots; ++s) {
-            int vid = owner[s];
-            if (vid == pin_a || vid == pin_b) continue;
-            if (victim < 0 || birth[vid] < birth[owner[victim]]) victim = s;
-        }
-        int idx;
-        if (!free_spill.empty()) { idx = free_spill.back(); free_spill.pop_back(); }
-        else idx = out.n_spill++;
-        out.ops.push_back({OP_SPILL, victim, idx, 0});
-        where[owner[victim]] = -(idx + 1);
-        owner[victim] = -1;
-        return victim;
-    }
-
-    void make_resident(int vid, int pin)
-    {
-        if (where[vid] >= 0) return;
-        int idx = -where[vid] - 1;
-        int s = acquire(vid, pin);
-        out.ops.push_back({OP_FILL, s, idx, 0});
-        free_spill.push_back(idx);
-        where[vid] = s;
-        owner[s] = vid;
-    }
-
-    void release(int vid)
-    {
-        owner[where[vid]] = -1;
-        where[vid] = -1000000;
-    }
-
-    // Binary nodes: internal child with the larger need first, leaves last (a*b == b*a exactly, so
-    // the product is bit-identical to the reference's child order).  Nodes with more than two
-    // children keep Newick order, because the reference multiplies factors in that order
-    // (src/probability.cpp:211-217, src/gene_family_reconstructor.cpp:96-101) and a reassociated
-    // product could differ in the last bit.
-    int emit(int v)
-    {
-        std::vector<int> order;
-        for (int e = tree.child_offset[v]; e < tree.child_offset[v + 1]; ++e) order.push_back(tree.child_list[e]);
-        if (order.size() <= 2)
-            std::stable_sort(order.begin(), order.end(), [this](int a, int b) {
-                const int na = tree.is_leaf(a) ? -1 : need[a], nb = tree.is_leaf(b) ? -1 : need[b];
-                return na > nb;
-            });
-        int acc = -1;
-        for (int c : order) {
-            if (!tree.is_leaf(c)) {
-                int vid = emit(c);
-                make_resident(vid, acc);
-                if (acc < 0) {
-                    out.ops.push_back({OP_GEMM_SET, where[vid], where[vid], c});
-                    acc = vid;
-                }
-                else {
-                    make_resident(acc, vid);
-                    out.ops.push_back({OP_GEMM_MUL, where[acc], where[vid], c});
-                    release(vid);
-                }
-            }
-            else if (acc < 0) {
-                acc = new_vector();
-                int s = acquire(-1, -1);
-                where[acc] = s;
-                owner[s] = acc;
-                out.ops.push_back({OP_LEAF_SET, s, 0, c});
-            }
-            else {
-                make_resident(acc, -1);
-                out.ops.push_back({OP_LEAF_MUL, where[acc], 0, c});
-            }
-        }
-        make_resident(acc, -1);
-        out.ops.push_back({OP_RESCALE, where[acc], 0, v});
-        return acc;
-    }
-};
-
-// Copies and validates the caller's tree; returns an error text or nullptr.
-const char* import_tree(HostTree& t, const cafe_b200_tree* tree, int n_leaves)
-{
-    const int nn = tree->n_nodes;
-    t.n_nodes = nn;
-    t.parent.assign(tree->parent, tree->parent + nn);
-    t.child_offset.assign(tree->child_offset, tree->child_offset + nn + 1);
-    t.child_list.assign(tree->child_list, tree->child_list + (nn - 1));
-    t.leaf_col.assign(tree->leaf_col, tree->leaf_col + nn);
-    t.lambda_index.assign(tree->lambda_index, tree->lambda_index + nn);
-    t.branch.assign(tree->branch, tree->branch + nn);
-    t.branch_key.resize(nn);
-    t.n_internal = 0;
-    t.n_lambdas = 1;
-    if (t.child_offset[0] != 0 || t.child_offset[nn] != nn - 1) return "child_offset does not describe n_nodes-1 edges";
-    int leaves = 0;
-    for (int v = 0; v < nn; ++v) {
-        if ((t.parent[v] < 0) != (v == nn - 1)) return "the root must be the last node and the only one without parent";
-        if (v < nn - 1 && (t.parent[v] <= v || t.parent[v] >= nn)) return "children must precede their parent";
-        if (t.child_offset[v + 1] < t.child_offset[v]) return "child_offset not monotone";
-        for (int e = t.child_offset[v]; e < t.child_offset[v + 1]; ++e)
-            if (t.child_list[e] < 0 || t.child_list[e] >= v || t.parent[t.child_list[e]] != v) return "child_list inconsistent with parent";
-        if (t.is_leaf(v)) {
-            ++leaves;
-            if (n_leaves >= 0 && (t.leaf_col[v] < 0 || t.leaf_col[v] >= n_leaves)) return "leaf_col out of range";
-        }
-        else t.n_internal++;
-        if (t.lambda_index[v] < 0) return "negative lambda index";
-        t.n_lambdas = std::max(t.n_lambdas, t.lambda_index[v] + 1);
-        t.branch_key[v] = (long)(t.branch[v] * 1000);
-    }
-    if (n_leaves >= 0 && leaves != n_leaves) return "n_leaves does not match the tree";
-    if (t.is_leaf(nn - 1)) return "the root is a leaf";
-    return nullptr;
-}
-
-// Peephole over the schedule (pruning without error model): a leaf sibling that directly follows is
-// folded into the producing op.  The products formed are the same two-operand products in the same
-// order, so results are bit-identical to the unfused schedule.
-//   LEAF_SET(a,l1) LEAF_MUL(a,l2)  -> LEAF_SET2(a,l1,l2)
-//   GEMM_SET(a,c)  LEAF_MUL(a,l)   -> GEMM_SET_LEAF(a,c,l)
-// GEMM_MUL is never fused: (f1*f2)*leaf must not become f1*(f2*leaf).
-std::vector<FusedOp> fuse_schedule(const std::vector<Op>& ops, bool fuse)
-{
-    std::vector<FusedOp> out;
-    for (size_t i = 0; i < ops.size(); ++i) {
-        const Op& o = ops[i];
-        if (fuse && i + 1 < ops.size() && ops[i + 1].type == OP_LEAF_MUL && ops[i + 1].a == o.a) {
-            if (o.type == OP_LEAF_SET) { out.push_back({OP_LEAF_SET2, o.a, 0, o.node, ops[i + 1].node}); ++i; continue; }
-            if (o.type == OP_GEMM_SET) { out.push_back({OP_GEMM_SET_LEAF, o.a, o.b, o.node, ops[i + 1].node}); ++i; continue; }
-        }
-        out.push_back({o.type, o.a, o.b, o.node, -1});
-    }
-    return out;
-}
 
 template <typename T>
 cudaError_t dev_alloc(T** p, size_t n, bool zero = false)
@@ -248,50 +58,44 @@ cudaError_t dev_alloc(T** p, size_t n, bool zero = false)
     return e;
 }
 
+constexpr int FAMILY_PAD = 96;          // count rows are padded (zeros) to whole tiles of 16, 32 and 48 families
+constexpr int MAX_PARTIALS = 1024;
+
+// Offsets (bytes) of the per-evaluation parameter block: one pinned host image, one device copy per shard, moved
+// with a single cudaMemcpyAsync.  Small fixed-size tables first, the pow(coeff, j) rows last, so that only the
+// used prefix travels.
+struct ParamLayout {
+    size_t prior = 0, logprior = 0, catprobs = 0, mat_of = 0, pops = 0, leafrefs = 0, keys = 0, powc = 0, total = 0;
+};
+
 }  // namespace
 
-struct cafe_b200_ctx {
+// One device's share of the families and every device buffer the kernels touch.
+struct Shard {
     int device = 0;
+    int index = 0;
+    int64_t first = 0, n_families = 0;  // family range [first, first + n_families)
+    int64_t padded_families = 0;
     cudaStream_t stream = nullptr;
     cudaStream_t own_stream = nullptr;
     int sm_count = 0;
     int smem_optin = 0;
-    HostTree tree;
-    int n_leaves = 0, mf = 0, mrf = 0, n = 0, mb = 0, nr = 0, kpanels = 0, n_kchunks = 0;
-    int64_t n_families = 0;
-    int64_t n_tiles = 0;
     int max_count = 0;
-    Schedule sched;                     // reconstruction kernel: op list for n_slots slots
-    Schedule psched;                    // pruning kernel: op list for prune_slots slots (unfused form: used with an error model)
-    std::vector<FusedOp> fused;         // psched with leaf siblings fused: pruning without error model
-    int n_slots = 0, hw_slots = 0;              // reconstruction kernel (32-family tiles)
-    int prune_slots = 0, prune_hw_slots = 0;    // pruning kernel (n_groups x 16-family tiles)
-    int n_groups = 2;                   // consumer groups of the pruning kernel (3 when shared memory allows)
-    int n_stages = 4;                   // pruning ring depth
-    int rescale = 0;
-    int cap_k = 0;                      // categories the k-dependent buffers are sized for
-    size_t mp_stride = 0, mt_stride = 0;
     // device buffers
-    int32_t* d_counts = nullptr;
-    Op* d_ops = nullptr;
-    POp* d_pops = nullptr;              // [cap_k][pops_cap] per-category resolved pruning ops
-    int pops_cap = 0;
-    int n_pops = 0;                     // ops per category in the last staged evaluation
+    void* d_counts = nullptr;           // [padded_families][n_leaves] uint8 / uint16
+    void* d_raw = nullptr;              // staging for count uploads in the caller's element width
+    size_t raw_bytes = 0;
+    int* d_range = nullptr;             // [min, max] of an uploaded matrix
+    Op* d_ops = nullptr;                // reconstruction schedule
     int* d_leaf_col = nullptr;
     int* d_parent = nullptr;
-    int* d_child_offset = nullptr;
-    int* d_child_list = nullptr;
-    int* d_mat_of = nullptr;
+    int* d_internal = nullptr;          // [n_nodes] position among internal nodes, -1 for leaves
+    unsigned char* d_param = nullptr;   // the parameter block (ParamLayout)
     double* d_mp = nullptr;
     double* d_mt = nullptr;
-    KeyParams* d_keys = nullptr;
-    double* d_powc = nullptr;
     double* d_lgamma = nullptr;
     double* d_err = nullptr;
-    int err_rows = 0, err_ndev = 0;
-    double* d_prior = nullptr;
-    double* d_logprior = nullptr;
-    double* d_catprobs = nullptr;
+    size_t err_cap = 0;
     double* d_cat_lk = nullptr;
     uint8_t* d_fail = nullptr;
     double* d_family_lnl = nullptr;
@@ -299,15 +103,51 @@ struct cafe_b200_ctx {
     double* d_partial = nullptr;
     double* d_result = nullptr;
     double* d_scratch = nullptr;        // reconstruction spill area
-    double* d_pscratch = nullptr;       // pruning spill area [SMs][n_spill][tile families x LDV]
-    int* d_pscratch_exp = nullptr;
-    // pinned staging
-    unsigned char* h_stage = nullptr;
-    size_t h_stage_bytes = 0;
-    double* h_result = nullptr;
-    cudaEvent_t staged = nullptr;       // H2D copies of the last call have consumed h_stage
+    double* d_pscratch = nullptr;       // pruning: parked entries beyond tensor memory
+    uint8_t* d_ctab = nullptr;          // reconstruction: argmax tables of the tiles in flight
+    size_t ctab_bytes = 0;
+    int32_t* d_states = nullptr;
+    size_t states_cap = 0;
+    double* h_result = nullptr;         // pinned [2]
+    int* h_range = nullptr;             // pinned [2]
+    cudaEvent_t staged = nullptr;       // H2D copy of the last parameter block has been consumed
     cudaEvent_t ev[5] = {nullptr, nullptr, nullptr, nullptr, nullptr};
     bool ev_valid[5] = {false, false, false, false, false};
+};
+
+struct cafe_b200_ctx {
+    std::vector<Shard*> shards;
+    HostTree tree;
+    int n_leaves = 0, mf = 0, mrf = 0, n = 0, mb = 0, nr = 0, kpanels = 0, n_kchunks = 0, lg_len = 0;
+    int64_t n_families = 0;
+    int cnt_width = 1;                  // bytes per leaf count on the device
+    int max_count = 0;
+    // reconstruction kernel (32-family tiles, slot machine)
+    Schedule sched;
+    int n_slots = 0, hw_slots = 0;
+    // pruning kernel (stack machine)
+    Program prog;
+    PruneGeom geom = {0, 4, 2, 2, 2};
+    int n_stages = 4;
+    int cnt_smem_bytes = 0;
+    int ops_smem_bytes = 0;             // the program of one category, staged in shared memory when it fits
+    int tmem_cap = 0;                   // parked entries per warp tensor memory can hold
+    int tmem_limit = -1;                // test hook: cap on tmem_cap (CAFE_B200_OPT_MAX_SLOTS)
+    int tmem_entries = 0, n_gspill = 0, tmem_cols = 0, prune_smem = 0;
+    int rescale = 0;
+    int cap_k = 0;                      // categories the k-dependent buffers are sized for
+    size_t mp_stride = 0, mt_stride = 0;
+    ParamLayout lay;
+    // pinned host image of the parameter block and the error model
+    unsigned char* h_param = nullptr;
+    size_t h_param_bytes = 0;
+    size_t param_used = 0;
+    int n_keys = 0;
+    std::vector<double> err_host;       // last uploaded table
+    double* h_err = nullptr;
+    size_t h_err_cap = 0;
+    int err_rows = 0, err_ndev = 0;
+    bool has_err = false;
     int64_t launches = 0;
     int64_t evals = 0;
     std::string error;
@@ -328,56 +168,203 @@ int fail(cafe_b200_ctx* ctx, int code, const std::string& msg)
         if (e__ != cudaSuccess) return fail(ctx, CAFE_B200_ERR_CUDA, std::string(#call) + ": " + cudaGetErrorString(e__)); \
     } while (0)
 
+cudaError_t prune_dispatch(const cafe_b200_ctx* c, const PruneParams& p, int grid, cudaStream_t s, bool attr_only)
+{
+    switch (c->geom.rb) {
+    case 1: return prune_launch_rb1(c->geom, p, grid, c->prune_smem, s, attr_only);
+    case 2: return prune_launch_rb2(c->geom, p, grid, c->prune_smem, s, attr_only);
+    case 3: return prune_launch_rb3(c->geom, p, grid, c->prune_smem, s, attr_only);
+    case 4: return prune_launch_rb4(c->geom, p, grid, c->prune_smem, s, attr_only);
+    case 5: return prune_launch_rb5(c->geom, p, grid, c->prune_smem, s, attr_only);
+    case 6: return prune_launch_rb6(c->geom, p, grid, c->prune_smem, s, attr_only);
+    case 7: return prune_launch_rb7(c->geom, p, grid, c->prune_smem, s, attr_only);
+    case 8: return prune_launch_rb8(c->geom, p, grid, c->prune_smem, s, attr_only);
+    }
+    return cudaErrorInvalidConfiguration;
+}
+
+template <int MB>
+cudaError_t pupko_attr_mb(int smem) { return cudaFuncSetAttribute(pupko_kernel<MB>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem); }
+
+template <int MB>
+int pupko_smem_mb(int slots) { return PupkoSmem<MB>::total_bytes(slots); }
+
+#define MB_SWITCH(mb, expr)                      \
+    switch (mb) {                                \
+    case 1: { constexpr int MB_ = 1; expr; } break; \
+    case 2: { constexpr int MB_ = 2; expr; } break; \
+    case 3: { constexpr int MB_ = 3; expr; } break; \
+    case 4: { constexpr int MB_ = 4; expr; } break; \
+    case 5: { constexpr int MB_ = 5; expr; } break; \
+    case 6: { constexpr int MB_ = 6; expr; } break; \
+    case 7: { constexpr int MB_ = 7; expr; } break; \
+    default: { constexpr int MB_ = 8; expr; } break; \
+    }
+
+// ------------------------------------------------------------------------------------------------------------------
+// planning
+// ------------------------------------------------------------------------------------------------------------------
+
+// Shared-memory plan of the pruning kernel: the geometry with the most consumer groups whose vectors, count tile and
+// at least a 3-stage matrix ring fit; the ring then takes what is left (up to MAX_RING_STAGES stages).
+bool plan_prune(cafe_b200_ctx* c, int smem_limit)
+{
+    const int depth = c->prog.depth;
+    const int cnt_tile = GFT * c->n_leaves * c->cnt_width;          // one group's count rows
+    std::vector<PruneGeom> candidates;
+    if (c->n <= 256) {
+        const int rb = (c->n + 31) / 32;
+        if (rb <= 5) candidates.push_back({rb, 4, 3, 2, 2});
+        candidates.push_back({rb, 4, 2, 2, 2});
+    }
+    else {
+        candidates.push_back({(c->n + 63) / 64, 8, 1, 1, 1});
+    }
+    if (const char* e = getenv("CAFE_B200_GEOM")) {
+        // experiments: "ng,cps,pw[,stages]" for the compiled geometries of this matrix size
+        int ng = 0, cps = 0, pw = 0, st = 0;
+        if (sscanf(e, "%d,%d,%d,%d", &ng, &cps, &pw, &st) >= 3) {
+            PruneGeom g = {candidates[0].rb, candidates[0].gw, ng, cps, pw};
+            if (prune_geometry_compiled(g)) candidates.insert(candidates.begin(), g);
+        }
+    }
+    int forced_stages = 0;
+    if (const char* e = getenv("CAFE_B200_GEOM")) {
+        int a, b, d, st = 0;
+        if (sscanf(e, "%d,%d,%d,%d", &a, &b, &d, &st) == 4) forced_stages = st;
+    }
+    // the leaf list is padded to an even number of 8-byte entries so that both parts of the program copy as 16-byte words
+    const int prog_bytes = (int)(c->prog.ops.size() * sizeof(POp) + ((c->prog.leaves.size() + 1) & ~size_t(1)) * sizeof(LeafRef)) + 16;
+    for (const PruneGeom& g : candidates) {
+        for (int variant = 0; variant < 4; ++variant) {
+            // preference: counts and program on chip; then drop the program, then the counts, then both
+            const bool with_counts = !(variant & 2), with_ops = !(variant & 1);
+            const int cnt = with_counts ? g.ng * cnt_tile : 0;
+            const int opsb = with_ops ? prog_bytes : 0;
+            const int fixed = pg_total_bytes(g.rb, g.gw, g.ng, g.cps, 0, cnt, depth) + opsb;
+            const int stage = pg_stage_bytes(g.rb, g.gw, g.cps);
+            int stages = (smem_limit - fixed) / stage;
+            stages = std::min(stages, MAX_RING_STAGES);
+            if (forced_stages > 0) stages = std::min(stages, forced_stages);
+            const int min_stages = (g.gw == 8) ? 2 : 3;
+            if (stages < min_stages) continue;
+            c->geom = g;
+            c->n_stages = stages;
+            c->cnt_smem_bytes = cnt;
+            c->ops_smem_bytes = opsb;
+            c->prune_smem = pg_total_bytes(g.rb, g.gw, g.ng, g.cps, stages, cnt, depth) + opsb;
+            c->tmem_cap = pg_tmem_capacity(g.rb, g.gw, g.ng);
+            return true;
+        }
+    }
+    return false;
+}
+
+// Parked-stack placement: the innermost entries (most frequently pushed and popped) live in tensor memory.
+void place_stack(cafe_b200_ctx* c)
+{
+    int cap = c->tmem_cap;
+    if (c->tmem_limit >= 0) cap = std::min(cap, c->tmem_limit);
+    c->tmem_entries = std::min(c->prog.depth, cap);
+    c->n_gspill = c->prog.depth - c->tmem_entries;
+    int cols = c->geom.ng * (c->geom.gw / 4) * c->tmem_entries * pg_frag_cols(c->geom.rb);
+    c->tmem_cols = 0;
+    if (cols > 0) {
+        c->tmem_cols = 32;
+        while (c->tmem_cols < cols) c->tmem_cols <<= 1;
+    }
+}
+
+int plan_pupko(cafe_b200_ctx* c, int smem_limit)
+{
+    if (c->mb > MAX_MB) { c->hw_slots = c->n_slots = 0; return 0; }      // reconstruction supports matrix sizes <= 256
+    int base = 0, slot = 0;
+    MB_SWITCH(c->mb, (base = PupkoSmem<MB_>::total_bytes(0), slot = PupkoSmem<MB_>::SLOT_BYTES));
+    c->hw_slots = std::min(MAX_SLOTS, (smem_limit - base) / slot);
+    c->n_slots = c->hw_slots;
+    return c->hw_slots;
+}
+
+// leaf references per category in the parameter block: padded to an even count (16-byte rows)
+size_t leafrefs_per_category(const cafe_b200_ctx* c) { return std::max<size_t>(2, (c->prog.leaves.size() + 1) & ~size_t(1)); }
+
+ParamLayout make_layout(const cafe_b200_ctx* c, int k)
+{
+    auto up = [](size_t x) { return (x + 15) & ~size_t(15); };
+    const size_t keys = (size_t)k * c->tree.n_nodes;
+    ParamLayout l;
+    size_t o = 0;
+    l.prior = o; o = up(o + (size_t)c->n * sizeof(double));
+    l.logprior = o; o = up(o + (size_t)c->n * sizeof(double));
+    l.catprobs = o; o = up(o + (size_t)k * sizeof(double));
+    l.mat_of = o; o = up(o + keys * sizeof(int));
+    l.pops = o; o = up(o + (size_t)k * c->prog.ops.size() * sizeof(POp));
+    l.leafrefs = o; o = up(o + (size_t)k * leafrefs_per_category(c) * sizeof(LeafRef));
+    l.keys = o; o = up(o + keys * sizeof(KeyParams));
+    l.powc = o; o = up(o + keys * c->n * sizeof(double));
+    l.total = o;
+    return l;
+}
+
+void free_category_buffers(Shard* s)
+{
+    cudaFree(s->d_param); cudaFree(s->d_mp); cudaFree(s->d_mt); cudaFree(s->d_cat_lk); cudaFree(s->d_fail);
+    s->d_param = nullptr; s->d_mp = s->d_mt = nullptr; s->d_cat_lk = nullptr; s->d_fail = nullptr;
+}
+
 int ensure_category_buffers(cafe_b200_ctx* c, int k)
 {
     if (k <= c->cap_k) return CAFE_B200_OK;
-    cudaFree(c->d_mat_of); cudaFree(c->d_mp); cudaFree(c->d_mt); cudaFree(c->d_keys); cudaFree(c->d_powc);
-    cudaFree(c->d_cat_lk); cudaFree(c->d_fail); cudaFree(c->d_catprobs); cudaFree(c->d_pops);
-    c->d_pops = nullptr;
-    c->d_mat_of = nullptr; c->d_mp = c->d_mt = nullptr; c->d_keys = nullptr; c->d_powc = nullptr;
-    c->d_cat_lk = nullptr; c->d_fail = nullptr; c->d_catprobs = nullptr;
+    if (k > 64) return fail(c, CAFE_B200_ERR_LIMIT, "more than 64 rate categories");
     c->cap_k = 0;
+    c->lay = make_layout(c, k);
     const size_t keys = (size_t)k * c->tree.n_nodes;
-    CUDA_TRY(c, dev_alloc(&c->d_mat_of, keys));
-    CUDA_TRY(c, dev_alloc(&c->d_mp, keys * c->mp_stride, true));
-    CUDA_TRY(c, dev_alloc(&c->d_mt, keys * c->mt_stride, true));
-    CUDA_TRY(c, dev_alloc(&c->d_keys, keys));
-    CUDA_TRY(c, dev_alloc(&c->d_powc, keys * c->n));
-    CUDA_TRY(c, dev_alloc(&c->d_cat_lk, (size_t)c->n_families * k));
-    CUDA_TRY(c, dev_alloc(&c->d_fail, (size_t)c->n_families * k, true));
-    CUDA_TRY(c, dev_alloc(&c->d_catprobs, (size_t)k));
-    c->pops_cap = (int)c->psched.ops.size();
-    CUDA_TRY(c, dev_alloc(&c->d_pops, (size_t)k * c->pops_cap));
-    // staging: keys + powc + mat_of + prior + logprior + catprobs + per-category ops
-    size_t need = keys * sizeof(KeyParams) + keys * c->n * sizeof(double) + keys * sizeof(int) + (2 * (size_t)c->n + k + 64) * sizeof(double)
-                  + (size_t)k * c->pops_cap * sizeof(POp) + 64;
-    if (need > c->h_stage_bytes) {
-        if (c->h_stage) cudaFreeHost(c->h_stage);
-        c->h_stage = nullptr;
-        CUDA_TRY(c, cudaMallocHost((void**)&c->h_stage, need));
-        c->h_stage_bytes = need;
+    for (Shard* s : c->shards) {
+        CUDA_TRY(c, cudaSetDevice(s->device));
+        CUDA_TRY(c, cudaStreamSynchronize(s->stream));
+        free_category_buffers(s);
+        CUDA_TRY(c, dev_alloc(&s->d_param, c->lay.total));
+        CUDA_TRY(c, dev_alloc(&s->d_mp, keys * c->mp_stride, true));
+        CUDA_TRY(c, dev_alloc(&s->d_mt, keys * c->mt_stride, true));
+        CUDA_TRY(c, dev_alloc(&s->d_cat_lk, (size_t)s->n_families * k));
+        CUDA_TRY(c, dev_alloc(&s->d_fail, (size_t)s->n_families * k, true));
+    }
+    if (c->lay.total > c->h_param_bytes) {
+        if (c->h_param) cudaFreeHost(c->h_param);
+        c->h_param = nullptr;
+        CUDA_TRY(c, cudaMallocHost((void**)&c->h_param, c->lay.total));
+        c->h_param_bytes = c->lay.total;
     }
     c->cap_k = k;
     return CAFE_B200_OK;
 }
 
-// Quantise keys, de-duplicate, stage per-key scalars and launch the matrix builder.
-int stage_and_build(cafe_b200_ctx* c, const double* lambdas, int n_lambdas, int k, const double* cat_probs, const double* prior,
-                    int n_prior)
+// ------------------------------------------------------------------------------------------------------------------
+// per-evaluation staging
+// ------------------------------------------------------------------------------------------------------------------
+
+// Quantise keys, de-duplicate, fill the pinned parameter block (once per call, shared by every shard).
+int stage_host(cafe_b200_ctx* c, const double* lambdas, int n_lambdas, int k, const double* cat_probs, const double* prior, int n_prior)
 {
+    NvtxRange r("cafe_b200: stage keys");
     if (n_lambdas < c->tree.n_lambdas) return fail(c, CAFE_B200_ERR_ARG, "n_lambdas smaller than the tree's lambda indices");
+    for (int i = 0; i < k * n_lambdas; ++i)
+        if (!std::isfinite(lambdas[i]) || lambdas[i] < 0 || lambdas[i] * 1e9 >= 9.2e18)
+            return fail(c, CAFE_B200_ERR_ARG, "lambda must be finite and non-negative (lambda::is_valid, src/lambda.cpp)");
     int rc = ensure_category_buffers(c, k);
     if (rc) return rc;
-    CUDA_TRY(c, cudaEventSynchronize(c->staged));
+    for (Shard* s : c->shards) CUDA_TRY(c, cudaEventSynchronize(s->staged));     // the previous block has left pinned memory
     const HostTree& t = c->tree;
     const size_t slots = (size_t)k * t.n_nodes;
-    unsigned char* h = c->h_stage;
-    KeyParams* h_keys = reinterpret_cast<KeyParams*>(h); h += slots * sizeof(KeyParams);
-    double* h_powc = reinterpret_cast<double*>(h); h += slots * c->n * sizeof(double);
-    double* h_prior = reinterpret_cast<double*>(h); h += (size_t)c->n * sizeof(double);
-    double* h_logprior = reinterpret_cast<double*>(h); h += (size_t)c->n * sizeof(double);
-    double* h_cat = reinterpret_cast<double*>(h); h += ((size_t)k + 8) * sizeof(double);
-    int* h_mat_of = reinterpret_cast<int*>(h);
+    unsigned char* h = c->h_param;
+    double* h_prior = reinterpret_cast<double*>(h + c->lay.prior);
+    double* h_logprior = reinterpret_cast<double*>(h + c->lay.logprior);
+    double* h_cat = reinterpret_cast<double*>(h + c->lay.catprobs);
+    int* h_mat_of = reinterpret_cast<int*>(h + c->lay.mat_of);
+    POp* h_pops = reinterpret_cast<POp*>(h + c->lay.pops);
+    LeafRef* h_leaf = reinterpret_cast<LeafRef*>(h + c->lay.leafrefs);
+    KeyParams* h_keys = reinterpret_cast<KeyParams*>(h + c->lay.keys);
+    double* h_powc = reinterpret_cast<double*>(h + c->lay.powc);
 
     std::map<std::pair<long, long>, int> seen;
     int n_keys = 0;
@@ -399,12 +386,18 @@ int stage_and_build(cafe_b200_ctx* c, const double* lambdas, int n_lambdas, int 
                 kp.log_alpha = std::log(alpha);
                 kp.coeff = coeff;
                 h_keys[n_keys] = kp;
-                double* pw = h_powc + (size_t)n_keys * c->n;
-                for (int j = 0; j < c->n; ++j) pw[j] = std::pow(coeff, (double)j);   // src/probability.cpp:125
                 it = seen.emplace(std::make_pair(kl, kt), n_keys++).first;
             }
             h_mat_of[cat * t.n_nodes + v] = it->second;
         }
+    }
+    // pow(coeff, j) rows from the host libm (src/probability.cpp:125): n_keys * N calls, threaded when there are many
+    const int n = c->n;
+    #pragma omp parallel for schedule(static) if ((size_t)n_keys * n > 20000) num_threads(8)
+    for (int key = 0; key < n_keys; ++key) {
+        const double coeff = h_keys[key].coeff;
+        double* pw = h_powc + (size_t)key * n;
+        for (int j = 0; j < n; ++j) pw[j] = std::pow(coeff, (double)j);
     }
     for (int j = 0; j < c->n; ++j) {
         const double pj = (prior && j < n_prior) ? prior[j] : 0.0;
@@ -412,231 +405,166 @@ int stage_and_build(cafe_b200_ctx* c, const double* lambdas, int n_lambdas, int 
         h_logprior[j] = std::log(pj);                                        // src/base_model.cpp:98
     }
     for (int cat = 0; cat < k; ++cat) h_cat[cat] = cat_probs ? cat_probs[cat] : 1.0;
-    // per-category pruning ops with matrix slots and count columns resolved
-    POp* h_pops = reinterpret_cast<POp*>((reinterpret_cast<uintptr_t>(h_mat_of + slots) + 15) & ~uintptr_t(15));   // POp is 16-byte aligned
-    if ((int)c->psched.ops.size() > c->pops_cap) return fail(c, CAFE_B200_ERR_ARG, "schedule grew after the category buffers were sized");
-    const std::vector<FusedOp> plain = c->d_err ? fuse_schedule(c->psched.ops, false) : std::vector<FusedOp>();
-    const std::vector<FusedOp>& fo = c->d_err ? plain : c->fused;
-    c->n_pops = (int)fo.size();
-    for (int cat = 0; cat < k; ++cat)
-        for (int o = 0; o < c->n_pops; ++o) {
+    // the pruning program with matrix slots, count columns and stack placement resolved per category
+    const size_t n_ops = c->prog.ops.size(), n_leaf = c->prog.leaves.size(), leaf_row = leafrefs_per_category(c);
+    for (int cat = 0; cat < k; ++cat) {
+        const int* mo = h_mat_of + (size_t)cat * t.n_nodes;
+        for (size_t o = 0; o < n_ops; ++o) {
+            const ProgOp& po = c->prog.ops[o];
             POp q;
-            q.type = fo[o].type; q.a = fo[o].a; q.b = fo[o].b; q.node = fo[o].node;
-            q.mat = h_mat_of[cat * t.n_nodes + fo[o].node];
-            q.col = t.leaf_col[fo[o].node];
-            q.mat2 = fo[o].node2 >= 0 ? h_mat_of[cat * t.n_nodes + fo[o].node2] : 0;
-            q.col2 = fo[o].node2 >= 0 ? t.leaf_col[fo[o].node2] : 0;
-            h_pops[(size_t)cat * c->n_pops + o] = q;
+            q.type = po.type; q.node = po.node; q.flags = po.flags;
+            q.mat = po.type == POP_GEMM ? mo[po.node] : 0;
+            q.park = po.stack >= c->n_gspill ? po.stack - c->n_gspill : -(po.stack + 1);
+            q.leaf_begin = po.leaf_begin; q.n_pre = po.n_pre; q.n_post = po.n_post;
+            h_pops[(size_t)cat * n_ops + o] = q;
         }
+        for (size_t i = 0; i < n_leaf; ++i) {
+            const int leaf = c->prog.leaves[i];
+            h_leaf[(size_t)cat * leaf_row + i] = {mo[leaf], t.leaf_col[leaf]};
+        }
+        for (size_t i = n_leaf; i < leaf_row; ++i) h_leaf[(size_t)cat * leaf_row + i] = {0, 0};
+    }
+    c->n_keys = n_keys;
+    c->param_used = c->lay.powc + (size_t)n_keys * c->n * sizeof(double);
+    (void)slots;
+    return CAFE_B200_OK;
+}
 
-    cudaStream_t s = c->stream;
-    CUDA_TRY(c, cudaMemcpyAsync(c->d_keys, h_keys, (size_t)n_keys * sizeof(KeyParams), cudaMemcpyHostToDevice, s));
-    CUDA_TRY(c, cudaMemcpyAsync(c->d_powc, h_powc, (size_t)n_keys * c->n * sizeof(double), cudaMemcpyHostToDevice, s));
-    CUDA_TRY(c, cudaMemcpyAsync(c->d_mat_of, h_mat_of, slots * sizeof(int), cudaMemcpyHostToDevice, s));
-    CUDA_TRY(c, cudaMemcpyAsync(c->d_prior, h_prior, (size_t)c->n * sizeof(double), cudaMemcpyHostToDevice, s));
-    CUDA_TRY(c, cudaMemcpyAsync(c->d_logprior, h_logprior, (size_t)c->n * sizeof(double), cudaMemcpyHostToDevice, s));
-    CUDA_TRY(c, cudaMemcpyAsync(c->d_catprobs, h_cat, (size_t)k * sizeof(double), cudaMemcpyHostToDevice, s));
-    CUDA_TRY(c, cudaMemcpyAsync(c->d_pops, h_pops, (size_t)k * c->n_pops * sizeof(POp), cudaMemcpyHostToDevice, s));
-    CUDA_TRY(c, cudaEventRecord(c->staged, s));
-
-    CUDA_TRY(c, cudaEventRecord(c->ev[0], s));
+// Upload the staged block to one shard and launch the matrix builder there.
+int shard_build(cafe_b200_ctx* c, Shard* s)
+{
+    CUDA_TRY(c, cudaSetDevice(s->device));
+    cudaStream_t st = s->stream;
+    CUDA_TRY(c, cudaMemcpyAsync(s->d_param, c->h_param, c->param_used, cudaMemcpyHostToDevice, st));
+    CUDA_TRY(c, cudaEventRecord(s->staged, st));
+    CUDA_TRY(c, cudaEventRecord(s->ev[0], st));
     MatrixBuildParams mp;
-    mp.n = c->n; mp.mf = c->mf; mp.nr = c->nr; mp.n_keys = n_keys;
-    mp.keys = c->d_keys; mp.powc = c->d_powc; mp.lgamma_tab = c->d_lgamma;
-    mp.mp = c->d_mp; mp.mt = c->d_mt; mp.mp_stride = c->mp_stride; mp.mt_stride = c->mt_stride;
+    mp.n = c->n; mp.mf = c->mf; mp.nr = c->nr; mp.n_keys = c->n_keys; mp.lg_len = c->lg_len;
+    mp.keys = reinterpret_cast<const KeyParams*>(s->d_param + c->lay.keys);
+    mp.powc = reinterpret_cast<const double*>(s->d_param + c->lay.powc);
+    mp.lgamma_tab = s->d_lgamma;
+    mp.mp = s->d_mp; mp.mt = s->d_mt; mp.mp_stride = c->mp_stride; mp.mt_stride = c->mt_stride;
     const int entries = ((c->n + 31) / 32) * 32 * (c->mf + 1);
     int bx = (entries + MB_THREADS - 1) / MB_THREADS;
     // keep the whole launch near a few waves: many keys -> fewer blocks per key (grid-stride inside)
-    const int target = std::max(1, (8 * c->sm_count + n_keys - 1) / n_keys);
+    const int target = std::max(1, (8 * s->sm_count + c->n_keys - 1) / std::max(1, c->n_keys));
     bx = std::max(1, std::min(bx, target));
-    dim3 grid(bx, n_keys);
-    const size_t smem = (LGAMMA_TABLE + c->n) * sizeof(double);
-    bd_matrix_kernel<<<grid, MB_THREADS, smem, s>>>(mp);
+    dim3 grid(bx, std::max(1, c->n_keys));
+    const size_t smem = ((size_t)c->lg_len + c->n) * sizeof(double);
+    bd_matrix_kernel<<<grid, MB_THREADS, smem, st>>>(mp);
     CUDA_TRY(c, cudaGetLastError());
     c->launches++;
-    CUDA_TRY(c, cudaEventRecord(c->ev[1], s));
-    c->ev_valid[0] = c->ev_valid[1] = true;
+    CUDA_TRY(c, cudaEventRecord(s->ev[1], st));
+    s->ev_valid[0] = s->ev_valid[1] = true;
     return CAFE_B200_OK;
 }
 
-template <int MB, int NG>
-int launch_prune_mbg(cafe_b200_ctx* c, const PruneParams& p)
+int stage_and_build(cafe_b200_ctx* c, const double* lambdas, int n_lambdas, int k, const double* cat_probs, const double* prior, int n_prior)
 {
-    using L = PruneSmem<MB, NG>;
-    const int smem = L::total_bytes(c->prune_slots, c->n_stages);
-    CUDA_TRY(c, cudaFuncSetAttribute(prune_kernel<MB, NG>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
-    const int64_t items = p.n_tiles * p.n_categories;        // one item = one tile of NG x 16 families of one category
-    const int grid = (int)std::min<int64_t>(items, c->sm_count);
-    prune_kernel<MB, NG><<<grid, prune_threads(NG), smem, c->stream>>>(p);
-    CUDA_TRY(c, cudaGetLastError());
-    c->launches++;
+    int rc = stage_host(c, lambdas, n_lambdas, k, cat_probs, prior, n_prior);
+    if (rc) return rc;
+    NvtxRange r("cafe_b200: build matrices");
+    for (Shard* s : c->shards) {
+        rc = shard_build(c, s);
+        if (rc) return rc;
+    }
     return CAFE_B200_OK;
 }
 
-template <int MB>
-int launch_prune_mb(cafe_b200_ctx* c, const PruneParams& p)
+int launch_prune(cafe_b200_ctx* c, Shard* s, int k, int mode, double* root_out)
 {
-    return c->n_groups == 3 ? launch_prune_mbg<MB, 3>(c, p) : launch_prune_mbg<MB, 2>(c, p);
-}
-
-int launch_prune(cafe_b200_ctx* c, int k, int mode, double* root_out)
-{
-    if (c->n_families == 0) return CAFE_B200_OK;
-    const int pft = c->n_groups * GFT;
+    if (s->n_families == 0) return CAFE_B200_OK;
+    const int pft = c->geom.ng * GFT;
     PruneParams p;
     memset(&p, 0, sizeof(p));
-    p.n_families = c->n_families; p.n_leaves = c->n_leaves; p.n_nodes = c->tree.n_nodes; p.n_categories = k;
-    p.mf = c->mf; p.mrf = c->mrf; p.n_ops = c->n_pops; p.n_kchunks = c->n_kchunks; p.mode = mode;
-    p.rescale = c->rescale; p.n_spill = std::max(1, c->psched.n_spill); p.err_rows = c->err_rows; p.err_ndev = c->err_ndev;
-    p.counts_in_smem = (pft * c->n_leaves * 2 <= PRUNE_CNT_CAP_BYTES) ? 1 : 0;
-    p.n_slots = c->prune_slots; p.n_tiles = (c->n_families + pft - 1) / pft;
-    // c->n_stages counts 10 KB chunks of ring memory; the kernel's stages hold CPS chunks each
-    p.n_stages = c->n_stages / CPS; p.stage_shift = p.n_stages == 4 ? 2 : (p.n_stages == 2 ? 1 : 0);
-    p.ops = c->d_pops; p.counts = c->d_counts;
-    p.mp = c->d_mp; p.mt = c->d_mt; p.mp_stride = c->mp_stride; p.mt_stride = c->mt_stride;
-    p.err = c->d_err; p.prior = c->d_prior; p.logprior = c->d_logprior; p.cat_probs = c->d_catprobs;
-    p.scratch = c->d_pscratch; p.scratch_exp = c->d_pscratch_exp;
-    p.cat_lk = c->d_cat_lk; p.fail = c->d_fail; p.root_out = root_out;
-    switch (c->mb) {
-    case 1: return launch_prune_mb<1>(c, p);
-    case 2: return launch_prune_mb<2>(c, p);
-    case 3: return launch_prune_mb<3>(c, p);
-    case 4: return launch_prune_mb<4>(c, p);
-    case 5: return launch_prune_mb<5>(c, p);
-    case 6: return launch_prune_mb<6>(c, p);
-    case 7: return launch_prune_mb<7>(c, p);
-    case 8: return launch_prune_mb<8>(c, p);
-    }
-    return fail(c, CAFE_B200_ERR_LIMIT, "matrix size not supported");
+    p.n_families = s->n_families; p.n_leaves = c->n_leaves; p.n_nodes = c->tree.n_nodes; p.n_categories = k;
+    p.mf = c->mf; p.mrf = c->mrf; p.n_ops = (int)c->prog.ops.size(); p.n_leafrefs = (int)leafrefs_per_category(c);
+    p.n_kchunks = c->n_kchunks; p.mode = mode;
+    p.rescale = c->rescale; p.err_rows = c->err_rows; p.err_ndev = c->err_ndev;
+    p.counts_in_smem = c->cnt_smem_bytes > 0 ? 1 : 0; p.cnt_smem_bytes = c->cnt_smem_bytes; p.cnt_width = c->cnt_width;
+    p.ops_in_smem = c->ops_smem_bytes > 0 ? 1 : 0;
+    p.n_stages = c->n_stages; p.depth = c->prog.depth; p.n_gspill = c->n_gspill; p.tmem_entries = c->tmem_entries; p.tmem_cols = c->tmem_cols;
+    p.n_tiles = (s->n_families + pft - 1) / pft;
+    p.ops = reinterpret_cast<const POp*>(s->d_param + c->lay.pops);
+    p.leaves = reinterpret_cast<const LeafRef*>(s->d_param + c->lay.leafrefs);
+    p.counts = s->d_counts;
+    p.mp = s->d_mp; p.mt = s->d_mt; p.mp_stride = c->mp_stride; p.mt_stride = c->mt_stride;
+    p.err = c->has_err ? s->d_err : nullptr;
+    p.prior = reinterpret_cast<const double*>(s->d_param + c->lay.prior);
+    p.logprior = reinterpret_cast<const double*>(s->d_param + c->lay.logprior);
+    p.cat_probs = reinterpret_cast<const double*>(s->d_param + c->lay.catprobs);
+    p.scratch = s->d_pscratch;
+    p.cat_lk = s->d_cat_lk; p.fail = s->d_fail; p.root_out = root_out;
+    const int64_t items = p.n_tiles * p.n_categories;        // one item = one tile of NG x 16 families of one category
+    const int grid = (int)std::min<int64_t>(items, s->sm_count);
+    CUDA_TRY(c, prune_dispatch(c, p, grid, s->stream, false));
+    c->launches++;
+    return CAFE_B200_OK;
 }
 
-template <int MB>
-int launch_pupko_mb(cafe_b200_ctx* c, const PupkoParams& p)
+int launch_pupko(cafe_b200_ctx* c, Shard* s, int k)
 {
-    using L = PupkoSmem<MB>;
-    const int smem = L::total_bytes(c->n_slots);
-    CUDA_TRY(c, cudaFuncSetAttribute(pupko_kernel<MB>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
-    const int64_t items = p.n_tiles * p.n_categories;
-    const int grid = (int)std::min<int64_t>(items, c->sm_count);
-    pupko_kernel<MB><<<grid, PRUNE_THREADS, smem, c->stream>>>(p);
+    if (s->n_families == 0) return CAFE_B200_OK;
+    const HostTree& t = c->tree;
+    const int64_t n_tiles = (s->n_families + FT - 1) / FT;
+    const int grid = (int)std::min<int64_t>(n_tiles * k, s->sm_count);
+    const size_t n_states = (size_t)s->n_families * k * t.n_internal;
+    const size_t ctab = (size_t)grid * t.n_internal * FT * c->nr;
+    if (ctab > s->ctab_bytes) {
+        CUDA_TRY(c, cudaStreamSynchronize(s->stream));
+        cudaFree(s->d_ctab); s->d_ctab = nullptr; s->ctab_bytes = 0;
+        CUDA_TRY(c, dev_alloc(&s->d_ctab, ctab));
+        s->ctab_bytes = ctab;
+    }
+    if (n_states > s->states_cap) {
+        CUDA_TRY(c, cudaStreamSynchronize(s->stream));
+        cudaFree(s->d_states); s->d_states = nullptr; s->states_cap = 0;
+        CUDA_TRY(c, dev_alloc(&s->d_states, n_states));
+        s->states_cap = n_states;
+    }
+    PupkoParams p;
+    memset(&p, 0, sizeof(p));
+    p.n_families = s->n_families; p.n_leaves = c->n_leaves; p.n_nodes = t.n_nodes; p.n_internal = t.n_internal; p.n_categories = k;
+    p.mf = c->mf; p.mrf = c->mrf; p.n_ops = (int)c->sched.ops.size(); p.n_kchunks = c->n_kchunks;
+    p.n_spill = std::max(1, c->sched.n_spill); p.n_slots = c->n_slots;
+    p.counts_in_smem = (FT * c->n_leaves * 2 <= CNT_CAP_BYTES) ? 1 : 0; p.cnt_width = c->cnt_width;
+    p.n_tiles = n_tiles; p.ops = s->d_ops; p.counts = s->d_counts; p.leaf_col = s->d_leaf_col; p.parent = s->d_parent;
+    p.internal_idx = s->d_internal; p.mat_of = reinterpret_cast<const int*>(s->d_param + c->lay.mat_of);
+    p.mt = s->d_mt; p.mt_stride = c->mt_stride; p.prior = reinterpret_cast<const double*>(s->d_param + c->lay.prior);
+    p.scratch = s->d_scratch; p.ctab = s->d_ctab; p.states = s->d_states;
+    int smem = 0;
+    MB_SWITCH(c->mb, (smem = PupkoSmem<MB_>::total_bytes(c->n_slots), pupko_kernel<MB_><<<grid, PRUNE_THREADS, smem, s->stream>>>(p)));
     CUDA_TRY(c, cudaGetLastError());
     c->launches++;
     return CAFE_B200_OK;
 }
 
-int launch_pupko(cafe_b200_ctx* c, int k, int32_t* states_host)
+// (Re)build the reconstruction schedule for n_slots slots and size the spill scratch of both kernels on every shard.
+int upload_plans(cafe_b200_ctx* c)
 {
-    if (c->n_families == 0) return CAFE_B200_OK;
-    const HostTree& t = c->tree;
-    std::vector<int> internal_idx(t.n_nodes, -1);
-    int ni = 0;
-    for (int v = 0; v < t.n_nodes; ++v) if (!t.is_leaf(v)) internal_idx[v] = ni++;
-    int* d_internal = nullptr;
-    uint8_t* d_ctab = nullptr;
-    int32_t* d_states = nullptr;
-    const size_t n_states = (size_t)c->n_families * k * t.n_internal;
-    const int grid = (int)std::min<int64_t>(c->n_tiles * k, c->sm_count);
-    int rc = CAFE_B200_OK;
-    cudaError_t e = dev_alloc(&d_internal, (size_t)t.n_nodes);
-    if (e == cudaSuccess) e = cudaMemcpyAsync(d_internal, internal_idx.data(), t.n_nodes * sizeof(int), cudaMemcpyHostToDevice, c->stream);
-    if (e == cudaSuccess) e = dev_alloc(&d_ctab, (size_t)grid * t.n_nodes * FT * c->nr);
-    if (e == cudaSuccess) e = dev_alloc(&d_states, n_states);
-    if (e == cudaSuccess) {
-        PupkoParams p;
-        memset(&p, 0, sizeof(p));
-        p.n_families = c->n_families; p.n_leaves = c->n_leaves; p.n_nodes = t.n_nodes; p.n_internal = t.n_internal; p.n_categories = k;
-        p.mf = c->mf; p.mrf = c->mrf; p.n_ops = (int)c->sched.ops.size(); p.n_kchunks = c->n_kchunks;
-        p.n_spill = std::max(1, c->sched.n_spill); p.n_slots = c->n_slots;
-        p.counts_in_smem = (FT * c->n_leaves * 2 <= CNT_CAP_BYTES) ? 1 : 0;
-        p.n_tiles = c->n_tiles; p.ops = c->d_ops; p.counts = c->d_counts; p.leaf_col = c->d_leaf_col; p.parent = c->d_parent;
-        p.internal_idx = d_internal; p.mat_of = c->d_mat_of; p.mt = c->d_mt; p.mt_stride = c->mt_stride; p.prior = c->d_prior;
-        p.scratch = c->d_scratch; p.ctab = d_ctab; p.states = d_states;
-        switch (c->mb) {
-        case 1: rc = launch_pupko_mb<1>(c, p); break;
-        case 2: rc = launch_pupko_mb<2>(c, p); break;
-        case 3: rc = launch_pupko_mb<3>(c, p); break;
-        case 4: rc = launch_pupko_mb<4>(c, p); break;
-        case 5: rc = launch_pupko_mb<5>(c, p); break;
-        case 6: rc = launch_pupko_mb<6>(c, p); break;
-        case 7: rc = launch_pupko_mb<7>(c, p); break;
-        default: rc = launch_pupko_mb<8>(c, p); break;
+    if (c->n_slots >= 2) c->sched = ScheduleBuilder(c->tree, c->n_slots).build();
+    place_stack(c);
+    const size_t ldv = ldv_of(std::min(c->mb, MAX_MB));
+    const size_t consumer_threads = (size_t)c->geom.ng * c->geom.gw * 32;
+    for (Shard* s : c->shards) {
+        CUDA_TRY(c, cudaSetDevice(s->device));
+        CUDA_TRY(c, cudaStreamSynchronize(s->stream));
+        cudaFree(s->d_ops); cudaFree(s->d_scratch); cudaFree(s->d_pscratch);
+        s->d_ops = nullptr; s->d_scratch = nullptr; s->d_pscratch = nullptr;
+        if (c->n_slots >= 2) {
+            CUDA_TRY(c, dev_alloc(&s->d_ops, c->sched.ops.size()));
+            CUDA_TRY(c, cudaMemcpy(s->d_ops, c->sched.ops.data(), c->sched.ops.size() * sizeof(Op), cudaMemcpyHostToDevice));
+            CUDA_TRY(c, dev_alloc(&s->d_scratch, (size_t)s->sm_count * std::max(1, c->sched.n_spill) * FT * ldv, true));
         }
-        if (rc == CAFE_B200_OK) {
-            e = cudaEventRecord(c->ev[4], c->stream);
-            if (e == cudaSuccess) e = cudaMemcpyAsync(states_host, d_states, n_states * sizeof(int32_t), cudaMemcpyDeviceToHost, c->stream);
-            if (e == cudaSuccess) e = cudaStreamSynchronize(c->stream);
-        }
+        CUDA_TRY(c, dev_alloc(&s->d_pscratch, (size_t)s->sm_count * std::max(1, c->n_gspill) * consumer_threads * 4 * c->geom.rb, true));
     }
-    cudaStreamSynchronize(c->stream);
-    cudaFree(d_internal); cudaFree(d_ctab); cudaFree(d_states);
-    if (e != cudaSuccess) return fail(c, CAFE_B200_ERR_CUDA, std::string("pupko: ") + cudaGetErrorString(e));
-    return rc;
-}
-
-// Shared-memory budget of the two tree-walking kernels.  Pruning: two consumer groups (32-family tiles) with three
-// vector slots and the deepest ring that fits (8 stages, else 4), two slots as a last resort.  A three-group layout
-// (48-family tiles, two slots; CAFE_B200_GROUPS=3) exists for experiments: the third MMA warp per sub-partition helps
-// an isolated K loop (scripts/kloop_mix.cu: 0.81 vs 0.76 of the DMMA rate) but in the full kernel the 128-register
-// cap of 448 threads and the extra spills of a two-slot schedule cost more (measured 0.685 vs 0.706).
-template <int MB>
-bool plan_shared_memory_mb(cafe_b200_ctx* c)
-{
-    const int lim = c->smem_optin;
-    c->hw_slots = std::min(MAX_SLOTS, (lim - PupkoSmem<MB>::total_bytes(0)) / PupkoSmem<MB>::SLOT_BYTES);
-    c->prune_hw_slots = 0;
-    const char* e = getenv("CAFE_B200_GROUPS");
-    if (e && atoi(e) == 3)
-        for (int stages : {8, 4}) {
-            const int sl = PruneSmem<MB, 3>::max_slots(lim, stages);
-            if (sl >= 2) { c->n_groups = 3; c->n_stages = stages; c->prune_hw_slots = sl; break; }
-        }
-    if (!c->prune_hw_slots)
-        for (int stages : {8, 4}) {
-            const int sl = PruneSmem<MB, 2>::max_slots(lim, stages);
-            if (sl >= 3 || (stages == 4 && sl >= 2)) { c->n_groups = 2; c->n_stages = stages; c->prune_hw_slots = sl; break; }
-        }
-    c->n_slots = c->hw_slots;
-    c->prune_slots = c->prune_hw_slots;
-    return c->hw_slots >= 2 && c->prune_hw_slots >= 2;
-}
-
-bool plan_shared_memory(cafe_b200_ctx* c)
-{
-    switch (c->mb) {
-    case 1: return plan_shared_memory_mb<1>(c);
-    case 2: return plan_shared_memory_mb<2>(c);
-    case 3: return plan_shared_memory_mb<3>(c);
-    case 4: return plan_shared_memory_mb<4>(c);
-    case 5: return plan_shared_memory_mb<5>(c);
-    case 6: return plan_shared_memory_mb<6>(c);
-    case 7: return plan_shared_memory_mb<7>(c);
-    default: return plan_shared_memory_mb<8>(c);
-    }
-}
-
-// (Re)build the op lists (reconstruction: n_slots, pruning: prune_slots) and size the spill scratch for them.
-int upload_schedule(cafe_b200_ctx* c)
-{
-    c->sched = ScheduleBuilder(c->tree, c->n_slots).build();
-    c->psched = ScheduleBuilder(c->tree, c->prune_slots).build();
-    c->fused = fuse_schedule(c->psched.ops, true);
-    if ((int)c->psched.ops.size() > c->pops_cap) c->cap_k = 0;       // force the per-category op buffers to be re-sized
-    cudaFree(c->d_ops); cudaFree(c->d_scratch); cudaFree(c->d_pscratch); cudaFree(c->d_pscratch_exp);
-    c->d_ops = nullptr; c->d_scratch = nullptr; c->d_pscratch = nullptr; c->d_pscratch_exp = nullptr;
-    CUDA_TRY(c, dev_alloc(&c->d_ops, c->sched.ops.size()));
-    CUDA_TRY(c, cudaMemcpy(c->d_ops, c->sched.ops.data(), c->sched.ops.size() * sizeof(Op), cudaMemcpyHostToDevice));
-    const size_t ldv = ldv_of(c->mb);
-    CUDA_TRY(c, dev_alloc(&c->d_scratch, (size_t)c->sm_count * std::max(1, c->sched.n_spill) * FT * ldv, true));
-    const size_t pft = (size_t)c->n_groups * GFT, pnsp = (size_t)std::max(1, c->psched.n_spill);
-    CUDA_TRY(c, dev_alloc(&c->d_pscratch, (size_t)c->sm_count * pnsp * pft * ldv, true));
-    CUDA_TRY(c, dev_alloc(&c->d_pscratch_exp, (size_t)c->sm_count * pnsp * pft, true));
     return CAFE_B200_OK;
 }
 
 int check_counts(cafe_b200_ctx* c)
 {
     int hi = c->max_count;
-    if (c->d_err) {
+    if (c->has_err) {
         if (c->max_count >= c->err_rows) return fail(c, CAFE_B200_ERR_COUNT_RANGE, "a leaf count has no error-model row");
         hi += (c->err_ndev - 1) / 2;
     }
@@ -644,33 +572,110 @@ int check_counts(cafe_b200_ctx* c)
     return CAFE_B200_OK;
 }
 
-int run_eval(cafe_b200_ctx* c, const double* lambdas, int n_lambdas, const double* cat_probs, int k, const double* prior, int mode,
-             double* result_device)
+// Upload a count matrix in the caller's element width; narrow it to the device width and range-check it on the device.
+int upload_counts(cafe_b200_ctx* c, const void* counts, int count_bytes)
+{
+    NvtxRange r("cafe_b200: upload families");
+    if (count_bytes != 1 && count_bytes != 2 && count_bytes != 4) return fail(c, CAFE_B200_ERR_ARG, "count_bytes must be 1, 2 or 4");
+    const size_t row = (size_t)c->n_leaves;
+    for (Shard* s : c->shards) {
+        if (s->n_families == 0) continue;
+        CUDA_TRY(c, cudaSetDevice(s->device));
+        const size_t total = (size_t)s->n_families * row;
+        const unsigned char* src = static_cast<const unsigned char*>(counts) + (size_t)s->first * row * count_bytes;
+        s->h_range[0] = INT_MAX; s->h_range[1] = INT_MIN;
+        CUDA_TRY(c, cudaMemcpyAsync(s->d_range, s->h_range, 2 * sizeof(int), cudaMemcpyHostToDevice, s->stream));
+        const void* d_src = s->d_counts;
+        if (count_bytes == c->cnt_width) {
+            CUDA_TRY(c, cudaMemcpyAsync(s->d_counts, src, total * count_bytes, cudaMemcpyHostToDevice, s->stream));
+        }
+        else {
+            if (total * count_bytes > s->raw_bytes) {
+                CUDA_TRY(c, cudaStreamSynchronize(s->stream));
+                cudaFree(s->d_raw); s->d_raw = nullptr; s->raw_bytes = 0;
+                CUDA_TRY(c, cudaMalloc(&s->d_raw, total * count_bytes));
+                s->raw_bytes = total * count_bytes;
+            }
+            CUDA_TRY(c, cudaMemcpyAsync(s->d_raw, src, total * count_bytes, cudaMemcpyHostToDevice, s->stream));
+            d_src = s->d_raw;
+        }
+        const int blocks = (int)std::max<int64_t>(1, std::min<int64_t>(((int64_t)total / 4 + RED_THREADS - 1) / RED_THREADS, 8 * (int64_t)s->sm_count));
+        ingest_counts_kernel<<<blocks, RED_THREADS, 0, s->stream>>>(d_src, count_bytes, s->d_counts, c->cnt_width, (int64_t)total, c->mf, s->d_range);
+        CUDA_TRY(c, cudaGetLastError());
+        c->launches++;
+        CUDA_TRY(c, cudaMemcpyAsync(s->h_range, s->d_range, 2 * sizeof(int), cudaMemcpyDeviceToHost, s->stream));
+    }
+    int lo = INT_MAX, hi = 0;
+    for (Shard* s : c->shards) {
+        if (s->n_families == 0) continue;
+        CUDA_TRY(c, cudaSetDevice(s->device));
+        CUDA_TRY(c, cudaStreamSynchronize(s->stream));
+        lo = std::min(lo, s->h_range[0]);
+        hi = std::max(hi, s->h_range[1]);
+    }
+    // the context now holds the new matrix; out-of-range counts are refused here and again by every evaluation
+    c->max_count = hi;
+    if (lo < 0) { c->max_count = c->mf + 1; return fail(c, CAFE_B200_ERR_COUNT_RANGE, "negative leaf count"); }
+    if (hi > c->mf) return fail(c, CAFE_B200_ERR_COUNT_RANGE, "a leaf count exceeds max_family_size");
+    return CAFE_B200_OK;
+}
+
+int enqueue_eval(cafe_b200_ctx* c, const double* lambdas, int n_lambdas, const double* cat_probs, int k, const double* prior, int mode,
+                 double* result_device_single)
 {
     if (!c || !lambdas || k < 1 || n_lambdas < 1 || (mode != CAFE_B200_BASE_LOGMAX && mode != CAFE_B200_GAMMA_LINSUM))
         return fail(c, CAFE_B200_ERR_ARG, "bad argument to eval");
     if (mode == CAFE_B200_BASE_LOGMAX && k != 1) return fail(c, CAFE_B200_ERR_ARG, "base mode takes exactly one category");
     if (!prior) return fail(c, CAFE_B200_ERR_ARG, "prior is required");
-    CUDA_TRY(c, cudaSetDevice(c->device));
     int rc = check_counts(c);
     if (rc) return rc;
     rc = stage_and_build(c, lambdas, n_lambdas, k, cat_probs, prior, c->mrf);
     if (rc) return rc;
-    rc = launch_prune(c, k, mode, nullptr);
-    if (rc) return rc;
-    cudaStream_t s = c->stream;
-    CUDA_TRY(c, cudaEventRecord(c->ev[2], s));
-    const int blocks = (int)std::max<int64_t>(1, std::min<int64_t>((c->n_families + RED_THREADS - 1) / RED_THREADS, 1024));
-    finalize_kernel<<<blocks, RED_THREADS, 0, s>>>(c->n_families, k, mode, c->d_cat_lk, c->d_fail, c->d_family_lnl, c->d_family_fail, c->d_partial);
-    CUDA_TRY(c, cudaGetLastError());
-    final_sum_kernel<<<1, RED_THREADS, 0, s>>>(blocks, c->d_partial, result_device);
-    CUDA_TRY(c, cudaGetLastError());
-    c->launches += 2;
-    CUDA_TRY(c, cudaEventRecord(c->ev[3], s));
-    c->ev_valid[2] = c->ev_valid[3] = true;
-    c->ev_valid[4] = false;
+    NvtxRange r("cafe_b200: prune + reduce");
+    for (Shard* s : c->shards) {
+        CUDA_TRY(c, cudaSetDevice(s->device));
+        rc = launch_prune(c, s, k, mode, nullptr);
+        if (rc) return rc;
+        cudaStream_t st = s->stream;
+        CUDA_TRY(c, cudaEventRecord(s->ev[2], st));
+        const int blocks = (int)std::max<int64_t>(1, std::min<int64_t>((s->n_families + RED_THREADS - 1) / RED_THREADS, MAX_PARTIALS));
+        finalize_kernel<<<blocks, RED_THREADS, 0, st>>>(s->n_families, k, mode, s->d_cat_lk, s->d_fail, s->d_family_lnl, s->d_family_fail, s->d_partial);
+        CUDA_TRY(c, cudaGetLastError());
+        final_sum_kernel<<<1, RED_THREADS, 0, st>>>(blocks, s->d_partial, result_device_single ? result_device_single : s->d_result);
+        CUDA_TRY(c, cudaGetLastError());
+        c->launches += 2;
+        CUDA_TRY(c, cudaEventRecord(s->ev[3], st));
+        s->ev_valid[2] = s->ev_valid[3] = true;
+        s->ev_valid[4] = false;
+    }
     c->evals++;
     return CAFE_B200_OK;
+}
+
+int sync_all(cafe_b200_ctx* c)
+{
+    for (Shard* s : c->shards) {
+        CUDA_TRY(c, cudaSetDevice(s->device));
+        CUDA_TRY(c, cudaStreamSynchronize(s->stream));
+    }
+    return CAFE_B200_OK;
+}
+
+void destroy_shard(Shard* s)
+{
+    if (!s) return;
+    cudaSetDevice(s->device);
+    if (s->stream) cudaStreamSynchronize(s->stream);
+    cudaFree(s->d_counts); cudaFree(s->d_raw); cudaFree(s->d_range); cudaFree(s->d_ops); cudaFree(s->d_leaf_col); cudaFree(s->d_parent);
+    cudaFree(s->d_internal); cudaFree(s->d_lgamma); cudaFree(s->d_err); cudaFree(s->d_family_lnl); cudaFree(s->d_family_fail);
+    cudaFree(s->d_partial); cudaFree(s->d_result); cudaFree(s->d_scratch); cudaFree(s->d_pscratch); cudaFree(s->d_ctab); cudaFree(s->d_states);
+    free_category_buffers(s);
+    if (s->h_result) cudaFreeHost(s->h_result);
+    if (s->h_range) cudaFreeHost(s->h_range);
+    if (s->staged) cudaEventDestroy(s->staged);
+    for (auto& e : s->ev) if (e) cudaEventDestroy(e);
+    if (s->own_stream) cudaStreamDestroy(s->own_stream);
+    delete s;
 }
 
 }  // namespace
@@ -682,10 +687,10 @@ int cafe_b200_abi_version(void) { return CAFE_B200_ABI_VERSION; }
 void cafe_b200_get_limits(cafe_b200_limits* out)
 {
     if (!out) return;
-    out->max_matrix_size = 32 * MAX_MB;
+    out->max_matrix_size = 512;                 // likelihood evaluation; reconstruction: 32 * MAX_MB = 256
     out->max_categories = 64;
     out->max_nodes = 1 << 20;
-    out->families_per_tile = FT;
+    out->families_per_tile = MAX_GROUPS * GFT;
 }
 
 int cafe_b200_device_count(void)
@@ -697,43 +702,50 @@ int cafe_b200_device_count(void)
 
 const char* cafe_b200_last_error(const cafe_b200_ctx* ctx) { return ctx ? ctx->error.c_str() : g_create_error.c_str(); }
 
+void* cafe_b200_alloc_pinned(size_t bytes)
+{
+    void* p = nullptr;
+    if (cudaMallocHost(&p, std::max<size_t>(bytes, 1)) != cudaSuccess) { cudaGetLastError(); return nullptr; }
+    return p;
+}
+
+void cafe_b200_free_pinned(void* p)
+{
+    if (p) cudaFreeHost(p);
+}
+
 void cafe_b200_destroy(cafe_b200_ctx* c)
 {
     if (!c) return;
-    cudaSetDevice(c->device);
-    if (c->stream) cudaStreamSynchronize(c->stream);
-    cudaFree(c->d_counts); cudaFree(c->d_ops); cudaFree(c->d_leaf_col); cudaFree(c->d_parent); cudaFree(c->d_child_offset);
-    cudaFree(c->d_child_list); cudaFree(c->d_mat_of); cudaFree(c->d_mp); cudaFree(c->d_mt); cudaFree(c->d_keys); cudaFree(c->d_powc);
-    cudaFree(c->d_lgamma); cudaFree(c->d_err); cudaFree(c->d_prior); cudaFree(c->d_logprior); cudaFree(c->d_catprobs);
-    cudaFree(c->d_pops);
-    cudaFree(c->d_cat_lk); cudaFree(c->d_fail); cudaFree(c->d_family_lnl); cudaFree(c->d_family_fail); cudaFree(c->d_partial);
-    cudaFree(c->d_result); cudaFree(c->d_scratch); cudaFree(c->d_pscratch); cudaFree(c->d_pscratch_exp);
-    if (c->h_stage) cudaFreeHost(c->h_stage);
-    if (c->h_result) cudaFreeHost(c->h_result);
-    if (c->staged) cudaEventDestroy(c->staged);
-    for (auto& e : c->ev) if (e) cudaEventDestroy(e);
-    if (c->own_stream) cudaStreamDestroy(c->own_stream);
+    for (Shard* s : c->shards) destroy_shard(s);
+    if (c->h_param) cudaFreeHost(c->h_param);
+    if (c->h_err) cudaFreeHost(c->h_err);
     delete c;
 }
 
-int cafe_b200_create(cafe_b200_ctx** out, const cafe_b200_tree* tree, const int32_t* leaf_counts, int64_t n_families, int n_leaves,
-                     int max_family_size, int max_root_family_size, int device)
+int cafe_b200_create_multi(cafe_b200_ctx** out, const cafe_b200_tree* tree, const void* leaf_counts, int count_bytes, int64_t n_families,
+                           int n_leaves, int max_family_size, int max_root_family_size, const int* devices, int n_devices)
 {
-    if (!out || !tree || n_families < 0 || n_leaves < 1 || max_family_size < 1 || max_root_family_size < 1 || (n_families > 0 && !leaf_counts))
+    if (!out || !tree || n_families < 0 || n_leaves < 1 || max_family_size < 1 || max_root_family_size < 1 || (n_families > 0 && !leaf_counts) ||
+        !devices || n_devices < 1)
         return fail(nullptr, CAFE_B200_ERR_ARG, "bad argument to create");
     *out = nullptr;
     const int nn = tree->n_nodes;
     if (nn < 2 || !tree->parent || !tree->child_offset || !tree->child_list || !tree->leaf_col || !tree->branch || !tree->lambda_index)
         return fail(nullptr, CAFE_B200_ERR_ARG, "incomplete tree");
+    if (count_bytes != 1 && count_bytes != 2 && count_bytes != 4) return fail(nullptr, CAFE_B200_ERR_ARG, "count_bytes must be 1, 2 or 4");
     int ndev = 0;
     if (cudaGetDeviceCount(&ndev) != cudaSuccess || ndev == 0) {
         cudaGetLastError();
         return fail(nullptr, CAFE_B200_ERR_CUDA, "no CUDA device: this engine has no CPU fallback");
     }
-    if (device < 0 || device >= ndev) return fail(nullptr, CAFE_B200_ERR_ARG, "device ordinal out of range");
+    for (int i = 0; i < n_devices; ++i) {
+        if (devices[i] < 0 || devices[i] >= ndev) return fail(nullptr, CAFE_B200_ERR_ARG, "device ordinal out of range");
+        for (int j = 0; j < i; ++j)
+            if (devices[j] == devices[i]) return fail(nullptr, CAFE_B200_ERR_ARG, "a device is listed twice");
+    }
 
     cafe_b200_ctx* c = new cafe_b200_ctx();
-    c->device = device;
     HostTree& t = c->tree;
     {
         const char* why = import_tree(t, tree, n_leaves);
@@ -742,23 +754,14 @@ int cafe_b200_create(cafe_b200_ctx** out, const cafe_b200_tree* tree, const int3
     c->n_leaves = n_leaves; c->mf = max_family_size; c->mrf = max_root_family_size;
     c->n = std::max(c->mf, c->mrf) + 1;                                      // src/base_model.cpp:77
     c->n_families = n_families;
-    c->n_tiles = (n_families + FT - 1) / FT;
-    c->mb = (c->n + 31) / 32;
-    if (c->mb > MAX_MB || 2 * c->n + 2 > LGAMMA_TABLE) {
-        g_create_error = "matrix size beyond this build (max 256)";
+    if (c->n > 512) {
+        g_create_error = "matrix size beyond this build (max 512)";
         delete c;
         return CAFE_B200_ERR_LIMIT;
     }
-    c->nr = nr_of(c->mb);
-    c->kpanels = ((c->mf + 1 + 3) / 4 + PPS - 1) / PPS * PPS;
-    c->n_kchunks = c->kpanels / PPS;
-    c->mp_stride = (size_t)c->kpanels * c->nr * 4;
-    c->mt_stride = (size_t)c->kpanels * 4 * c->nr;      // columns padded to whole ring stages (zeros)
-    for (int64_t i = 0; i < n_families * n_leaves; ++i) {
-        if (leaf_counts[i] < 0) { g_create_error = "negative leaf count"; delete c; return CAFE_B200_ERR_COUNT_RANGE; }
-        c->max_count = std::max(c->max_count, (int)leaf_counts[i]);
-    }
-    if (c->max_count > c->mf) { g_create_error = "a leaf count exceeds max_family_size"; delete c; return CAFE_B200_ERR_COUNT_RANGE; }
+    c->cnt_width = c->mf <= 255 ? 1 : 2;
+    c->lg_len = 2 * c->n + 2;                    // lgamma arguments reach s + c <= 2 (N - 1)           src/probability.cpp:58-64
+    c->prog = ProgramBuilder(t).build();
 
 #define CREATE_TRY(call)                                                                      \
     do {                                                                                      \
@@ -770,81 +773,137 @@ int cafe_b200_create(cafe_b200_ctx** out, const cafe_b200_tree* tree, const int3
         }                                                                                     \
     } while (0)
 
-    CREATE_TRY(cudaSetDevice(device));
-    CREATE_TRY(cudaDeviceGetAttribute(&c->sm_count, cudaDevAttrMultiProcessorCount, device));
-    CREATE_TRY(cudaDeviceGetAttribute(&c->smem_optin, cudaDevAttrMaxSharedMemoryPerBlockOptin, device));
-    CREATE_TRY(cudaStreamCreateWithFlags(&c->own_stream, cudaStreamNonBlocking));
-    c->stream = c->own_stream;
-    CREATE_TRY(cudaEventCreateWithFlags(&c->staged, cudaEventDisableTiming));
-    CREATE_TRY(cudaEventRecord(c->staged, c->stream));
-    for (auto& e : c->ev) CREATE_TRY(cudaEventCreate(&e));
+    int smem_limit = INT_MAX;
+    for (int i = 0; i < n_devices; ++i) {
+        Shard* s = new Shard();
+        c->shards.push_back(s);
+        s->device = devices[i];
+        s->index = i;
+        s->first = n_families * i / n_devices;
+        s->n_families = n_families * (i + 1) / n_devices - s->first;
+        s->padded_families = (s->n_families + FAMILY_PAD - 1) / FAMILY_PAD * FAMILY_PAD + FAMILY_PAD;
+        CREATE_TRY(cudaSetDevice(s->device));
+        CREATE_TRY(cudaDeviceGetAttribute(&s->sm_count, cudaDevAttrMultiProcessorCount, s->device));
+        CREATE_TRY(cudaDeviceGetAttribute(&s->smem_optin, cudaDevAttrMaxSharedMemoryPerBlockOptin, s->device));
+        smem_limit = std::min(smem_limit, s->smem_optin);
+        CREATE_TRY(cudaStreamCreateWithFlags(&s->own_stream, cudaStreamNonBlocking));
+        s->stream = s->own_stream;
+        CREATE_TRY(cudaEventCreateWithFlags(&s->staged, cudaEventDisableTiming));
+        CREATE_TRY(cudaEventRecord(s->staged, s->stream));
+        for (auto& e : s->ev) CREATE_TRY(cudaEventCreate(&e));
+    }
 
-    if (!plan_shared_memory(c)) { g_create_error = "not enough shared memory for two vector slots"; cafe_b200_destroy(c); return CAFE_B200_ERR_LIMIT; }
-    if (upload_schedule(c) != CAFE_B200_OK) { g_create_error = c->error; cafe_b200_destroy(c); return CAFE_B200_ERR_CUDA; }
+    if (!plan_prune(c, smem_limit)) { g_create_error = "not enough shared memory for the pruning kernel at this matrix size / tree"; cafe_b200_destroy(c); return CAFE_B200_ERR_LIMIT; }
+    c->nr = pg_nr(c->geom.rb, c->geom.gw);
+    c->mb = c->nr / 32;
+    c->kpanels = ((c->mf + 1 + 3) / 4 + PPS - 1) / PPS * PPS;
+    c->n_kchunks = c->kpanels / PPS;
+    c->mp_stride = (size_t)c->kpanels * c->nr * 4;
+    c->mt_stride = (size_t)c->kpanels * 4 * c->nr;      // columns padded to whole ring stages (zeros)
+    plan_pupko(c, smem_limit);
 
-    CREATE_TRY(dev_alloc(&c->d_counts, (size_t)n_families * n_leaves));
-    if (n_families) CREATE_TRY(cudaMemcpy(c->d_counts, leaf_counts, (size_t)n_families * n_leaves * sizeof(int32_t), cudaMemcpyHostToDevice));
-    CREATE_TRY(dev_alloc(&c->d_leaf_col, (size_t)nn));
-    CREATE_TRY(cudaMemcpy(c->d_leaf_col, t.leaf_col.data(), nn * sizeof(int), cudaMemcpyHostToDevice));
-    CREATE_TRY(dev_alloc(&c->d_parent, (size_t)nn));
-    CREATE_TRY(cudaMemcpy(c->d_parent, t.parent.data(), nn * sizeof(int), cudaMemcpyHostToDevice));
-    CREATE_TRY(dev_alloc(&c->d_child_offset, (size_t)nn + 1));
-    CREATE_TRY(cudaMemcpy(c->d_child_offset, t.child_offset.data(), (nn + 1) * sizeof(int), cudaMemcpyHostToDevice));
-    CREATE_TRY(dev_alloc(&c->d_child_list, (size_t)nn));
-    CREATE_TRY(cudaMemcpy(c->d_child_list, t.child_list.data(), (nn - 1) * sizeof(int), cudaMemcpyHostToDevice));
-    std::vector<double> lg(LGAMMA_TABLE);
-    for (int i = 0; i < LGAMMA_TABLE; ++i) lg[i] = lgamma((double)i);        // src/probability.cpp:66-72
-    CREATE_TRY(dev_alloc(&c->d_lgamma, (size_t)LGAMMA_TABLE));
-    CREATE_TRY(cudaMemcpy(c->d_lgamma, lg.data(), LGAMMA_TABLE * sizeof(double), cudaMemcpyHostToDevice));
-    CREATE_TRY(dev_alloc(&c->d_prior, (size_t)c->n));
-    CREATE_TRY(dev_alloc(&c->d_logprior, (size_t)c->n));
-    CREATE_TRY(dev_alloc(&c->d_family_lnl, (size_t)n_families));
-    CREATE_TRY(dev_alloc(&c->d_family_fail, (size_t)n_families, true));
-    CREATE_TRY(dev_alloc(&c->d_partial, (size_t)2 * 1024));
-    CREATE_TRY(dev_alloc(&c->d_result, (size_t)2));
-    CREATE_TRY(cudaMallocHost((void**)&c->h_result, 2 * sizeof(double)));
+    std::vector<double> lg(c->lg_len);
+    for (int i = 0; i < c->lg_len; ++i) lg[i] = lgamma((double)i);           // src/probability.cpp:58-72 (table below 1024, libm above: same values)
+    std::vector<int> internal_idx(nn, -1);
+    {
+        int ni = 0;
+        for (int v = 0; v < nn; ++v) if (!t.is_leaf(v)) internal_idx[v] = ni++;
+    }
+    for (Shard* s : c->shards) {
+        CREATE_TRY(cudaSetDevice(s->device));
+        {
+            PruneParams dummy;
+            memset(&dummy, 0, sizeof(dummy));
+            CREATE_TRY(prune_dispatch(c, dummy, 1, s->stream, true));
+            if (c->hw_slots >= 2) {
+                int smem = 0;
+                cudaError_t e = cudaSuccess;
+                MB_SWITCH(c->mb, (smem = PupkoSmem<MB_>::total_bytes(c->hw_slots), e = pupko_attr_mb<MB_>(smem)));
+                CREATE_TRY(e);
+            }
+        }
+        CREATE_TRY(cudaMalloc(&s->d_counts, (size_t)s->padded_families * n_leaves * c->cnt_width));
+        CREATE_TRY(cudaMemsetAsync(s->d_counts, 0, (size_t)s->padded_families * n_leaves * c->cnt_width, s->stream));
+        CREATE_TRY(dev_alloc(&s->d_range, (size_t)2));
+        CREATE_TRY(cudaMallocHost((void**)&s->h_range, 2 * sizeof(int)));
+        CREATE_TRY(dev_alloc(&s->d_leaf_col, (size_t)nn));
+        CREATE_TRY(cudaMemcpy(s->d_leaf_col, t.leaf_col.data(), nn * sizeof(int), cudaMemcpyHostToDevice));
+        CREATE_TRY(dev_alloc(&s->d_parent, (size_t)nn));
+        CREATE_TRY(cudaMemcpy(s->d_parent, t.parent.data(), nn * sizeof(int), cudaMemcpyHostToDevice));
+        CREATE_TRY(dev_alloc(&s->d_internal, (size_t)nn));
+        CREATE_TRY(cudaMemcpy(s->d_internal, internal_idx.data(), nn * sizeof(int), cudaMemcpyHostToDevice));
+        CREATE_TRY(dev_alloc(&s->d_lgamma, (size_t)c->lg_len));
+        CREATE_TRY(cudaMemcpy(s->d_lgamma, lg.data(), c->lg_len * sizeof(double), cudaMemcpyHostToDevice));
+        CREATE_TRY(dev_alloc(&s->d_family_lnl, (size_t)s->n_families));
+        CREATE_TRY(dev_alloc(&s->d_family_fail, (size_t)s->n_families, true));
+        CREATE_TRY(dev_alloc(&s->d_partial, (size_t)2 * MAX_PARTIALS));
+        CREATE_TRY(dev_alloc(&s->d_result, (size_t)2));
+        CREATE_TRY(cudaMallocHost((void**)&s->h_result, 2 * sizeof(double)));
+    }
 #undef CREATE_TRY
+    if (upload_plans(c) != CAFE_B200_OK) { g_create_error = c->error; cafe_b200_destroy(c); return CAFE_B200_ERR_CUDA; }
+    if (n_families > 0) {
+        int rc = upload_counts(c, leaf_counts, count_bytes);
+        if (rc) { g_create_error = c->error; cafe_b200_destroy(c); return rc; }
+    }
     *out = c;
     return CAFE_B200_OK;
 }
 
-int cafe_b200_set_families(cafe_b200_ctx* c, const int32_t* leaf_counts, int64_t n_families)
+int cafe_b200_create(cafe_b200_ctx** out, const cafe_b200_tree* tree, const int32_t* leaf_counts, int64_t n_families, int n_leaves,
+                     int max_family_size, int max_root_family_size, int device)
+{
+    return cafe_b200_create_multi(out, tree, leaf_counts, 4, n_families, n_leaves, max_family_size, max_root_family_size, &device, 1);
+}
+
+int cafe_b200_n_devices(const cafe_b200_ctx* c) { return c ? (int)c->shards.size() : 0; }
+
+int cafe_b200_set_families_ex(cafe_b200_ctx* c, const void* leaf_counts, int count_bytes, int64_t n_families)
 {
     if (!c || !leaf_counts || n_families != c->n_families) return fail(c, CAFE_B200_ERR_ARG, "set_families: shape must match create");
-    const int64_t total = n_families * c->n_leaves;
-    if (total == 0) return CAFE_B200_OK;
-    CUDA_TRY(c, cudaSetDevice(c->device));
-    // upload, then range-check on the device (a host pass over 10^8 counts costs more than the copy)
-    int* d_range = reinterpret_cast<int*>(c->d_partial);      // scratch: [min, max]
-    const int init[2] = {INT_MAX, INT_MIN};
-    CUDA_TRY(c, cudaMemcpyAsync(d_range, init, sizeof(init), cudaMemcpyHostToDevice, c->stream));
-    CUDA_TRY(c, cudaMemcpyAsync(c->d_counts, leaf_counts, (size_t)total * sizeof(int32_t), cudaMemcpyHostToDevice, c->stream));
-    const int blocks = (int)std::max<int64_t>(1, std::min<int64_t>((total / 4 + RED_THREADS - 1) / RED_THREADS, 8 * (int64_t)c->sm_count));
-    count_range_kernel<<<blocks, RED_THREADS, 0, c->stream>>>(c->d_counts, total, d_range);
-    CUDA_TRY(c, cudaGetLastError());
-    c->launches++;
-    int range[2] = {0, 0};
-    CUDA_TRY(c, cudaMemcpyAsync(range, d_range, sizeof(range), cudaMemcpyDeviceToHost, c->stream));
-    CUDA_TRY(c, cudaStreamSynchronize(c->stream));
-    // the context now holds the new matrix; out-of-range counts are refused here and again by every evaluation
-    c->max_count = range[1];
-    if (range[0] < 0) { c->max_count = c->mf + 1; return fail(c, CAFE_B200_ERR_COUNT_RANGE, "negative leaf count"); }
-    if (range[1] > c->mf) return fail(c, CAFE_B200_ERR_COUNT_RANGE, "a leaf count exceeds max_family_size");
-    return CAFE_B200_OK;
+    if (n_families * c->n_leaves == 0) return CAFE_B200_OK;
+    return upload_counts(c, leaf_counts, count_bytes);
+}
+
+int cafe_b200_set_families(cafe_b200_ctx* c, const int32_t* leaf_counts, int64_t n_families)
+{
+    return cafe_b200_set_families_ex(c, leaf_counts, 4, n_families);
 }
 
 int cafe_b200_set_error_model(cafe_b200_ctx* c, const double* probs, int rows, int n_deviations)
 {
     if (!c) return CAFE_B200_ERR_ARG;
-    CUDA_TRY(c, cudaSetDevice(c->device));
-    CUDA_TRY(c, cudaStreamSynchronize(c->stream));
-    cudaFree(c->d_err);
-    c->d_err = nullptr; c->err_rows = c->err_ndev = 0;
-    if (!probs) return CAFE_B200_OK;
+    if (!probs) { c->has_err = false; c->err_rows = c->err_ndev = 0; c->err_host.clear(); return CAFE_B200_OK; }
     if (rows < 1 || n_deviations < 1 || (n_deviations % 2) == 0) return fail(c, CAFE_B200_ERR_ARG, "error model: odd number of deviations required");
-    CUDA_TRY(c, dev_alloc(&c->d_err, (size_t)rows * n_deviations));
-    CUDA_TRY(c, cudaMemcpy(c->d_err, probs, (size_t)rows * n_deviations * sizeof(double), cudaMemcpyHostToDevice));
-    c->err_rows = rows; c->err_ndev = n_deviations;
+    const size_t n = (size_t)rows * n_deviations;
+    // the epsilon optimiser calls this before every evaluation: nothing to do unless the table changed
+    if (c->has_err && rows == c->err_rows && n_deviations == c->err_ndev && c->err_host.size() == n &&
+        memcmp(c->err_host.data(), probs, n * sizeof(double)) == 0)
+        return CAFE_B200_OK;
+    if (n > c->h_err_cap) {
+        for (Shard* s : c->shards) { CUDA_TRY(c, cudaSetDevice(s->device)); CUDA_TRY(c, cudaStreamSynchronize(s->stream)); }
+        if (c->h_err) cudaFreeHost(c->h_err);
+        c->h_err = nullptr; c->h_err_cap = 0;
+        CUDA_TRY(c, cudaMallocHost((void**)&c->h_err, n * sizeof(double)));
+        c->h_err_cap = n;
+    }
+    else {
+        for (Shard* s : c->shards) CUDA_TRY(c, cudaEventSynchronize(s->staged));      // the previous table has left pinned memory
+    }
+    memcpy(c->h_err, probs, n * sizeof(double));
+    c->err_host.assign(probs, probs + n);
+    for (Shard* s : c->shards) {
+        CUDA_TRY(c, cudaSetDevice(s->device));
+        if (n > s->err_cap) {
+            CUDA_TRY(c, cudaStreamSynchronize(s->stream));
+            cudaFree(s->d_err); s->d_err = nullptr; s->err_cap = 0;
+            CUDA_TRY(c, dev_alloc(&s->d_err, n));
+            s->err_cap = n;
+        }
+        CUDA_TRY(c, cudaMemcpyAsync(s->d_err, c->h_err, n * sizeof(double), cudaMemcpyHostToDevice, s->stream));
+        CUDA_TRY(c, cudaEventRecord(s->staged, s->stream));
+    }
+    c->err_rows = rows; c->err_ndev = n_deviations; c->has_err = true;
     return CAFE_B200_OK;
 }
 
@@ -854,11 +913,9 @@ int cafe_b200_set_option(cafe_b200_ctx* c, int option, int value)
     if (option == CAFE_B200_OPT_RESCALE) { c->rescale = value ? 1 : 0; return CAFE_B200_OK; }
     if (option == CAFE_B200_OPT_MAX_SLOTS) {
         if (value < 2) return fail(c, CAFE_B200_ERR_ARG, "at least two slots are required");
-        CUDA_TRY(c, cudaSetDevice(c->device));
-        CUDA_TRY(c, cudaStreamSynchronize(c->stream));
         c->n_slots = std::min(value, c->hw_slots);
-        c->prune_slots = std::min(value, c->prune_hw_slots);
-        return upload_schedule(c);
+        c->tmem_limit = value - 2;               // pruning: value - 2 parked entries may use tensor memory, the rest spill
+        return upload_plans(c);
     }
     return fail(c, CAFE_B200_ERR_ARG, "unknown option");
 }
@@ -881,48 +938,104 @@ int cafe_b200_plan_schedule(const cafe_b200_tree* tree, int n_slots, int* ops_ou
     return CAFE_B200_OK;
 }
 
+int cafe_b200_plan_program(const cafe_b200_tree* tree, int* ops_out, int cap, int* n_ops, int* leaves_out, int leaves_cap, int* n_leaf_refs,
+                           int* depth)
+{
+    if (!tree || tree->n_nodes < 2 || !n_ops) return CAFE_B200_ERR_ARG;
+    HostTree t;
+    const char* why = import_tree(t, tree, -1);
+    if (why) { g_create_error = why; return CAFE_B200_ERR_ARG; }
+    Program p = ProgramBuilder(t).build();
+    *n_ops = (int)p.ops.size();
+    if (n_leaf_refs) *n_leaf_refs = (int)p.leaves.size();
+    if (depth) *depth = p.depth;
+    if (ops_out) {
+        if (cap < (int)p.ops.size()) return CAFE_B200_ERR_ARG;
+        for (size_t i = 0; i < p.ops.size(); ++i) {
+            const ProgOp& o = p.ops[i];
+            int* q = ops_out + 7 * i;
+            q[0] = o.type; q[1] = o.node; q[2] = o.flags; q[3] = o.stack; q[4] = o.leaf_begin; q[5] = o.n_pre; q[6] = o.n_post;
+        }
+    }
+    if (leaves_out) {
+        if (leaves_cap < (int)p.leaves.size()) return CAFE_B200_ERR_ARG;
+        std::copy(p.leaves.begin(), p.leaves.end(), leaves_out);
+    }
+    return CAFE_B200_OK;
+}
+
 int cafe_b200_set_stream(cafe_b200_ctx* c, void* cuda_stream)
 {
     if (!c) return CAFE_B200_ERR_ARG;
-    CUDA_TRY(c, cudaSetDevice(c->device));
-    CUDA_TRY(c, cudaStreamSynchronize(c->stream));
-    c->stream = (cudaStream_t)cuda_stream;          // NULL is the legacy default stream, as in the CUDA runtime
-    CUDA_TRY(c, cudaEventRecord(c->staged, c->stream));
+    if (c->shards.size() != 1) return fail(c, CAFE_B200_ERR_ARG, "set_stream: the context spans several devices");
+    Shard* s = c->shards[0];
+    CUDA_TRY(c, cudaSetDevice(s->device));
+    CUDA_TRY(c, cudaStreamSynchronize(s->stream));
+    s->stream = (cudaStream_t)cuda_stream;          // NULL is the legacy default stream, as in the CUDA runtime
+    CUDA_TRY(c, cudaEventRecord(s->staged, s->stream));
     return CAFE_B200_OK;
 }
 
 int cafe_b200_eval_device(cafe_b200_ctx* c, const double* lambdas, int n_lambdas, const double* cat_probs, int k, const double* prior,
                           int mode, double* result_device)
 {
+    if (!c) return CAFE_B200_ERR_ARG;
     if (!result_device) return fail(c, CAFE_B200_ERR_ARG, "result_device is null");
-    return run_eval(c, lambdas, n_lambdas, cat_probs, k, prior, mode, result_device);
+    if (c->shards.size() != 1) return fail(c, CAFE_B200_ERR_ARG, "eval_device: the context spans several devices; use cafe_b200_eval");
+    return enqueue_eval(c, lambdas, n_lambdas, cat_probs, k, prior, mode, result_device);
 }
 
 int cafe_b200_eval(cafe_b200_ctx* c, const double* lambdas, int n_lambdas, const double* cat_probs, int k, const double* prior, int mode,
                    double* neg_lnl, double* family_lnl, double* cat_lk, int64_t* n_failed, int64_t* failed_idx, int64_t failed_cap)
 {
     if (!c || !neg_lnl) return fail(c, CAFE_B200_ERR_ARG, "neg_lnl is null");
-    int rc = run_eval(c, lambdas, n_lambdas, cat_probs, k, prior, mode, c->d_result);
+    NvtxRange r("cafe_b200_eval");
+    int rc = enqueue_eval(c, lambdas, n_lambdas, cat_probs, k, prior, mode, nullptr);
     if (rc) return rc;
-    cudaStream_t s = c->stream;
-    CUDA_TRY(c, cudaMemcpyAsync(c->h_result, c->d_result, 2 * sizeof(double), cudaMemcpyDeviceToHost, s));
-    if (family_lnl && c->n_families)
-        CUDA_TRY(c, cudaMemcpyAsync(family_lnl, c->d_family_lnl, (size_t)c->n_families * sizeof(double), cudaMemcpyDeviceToHost, s));
-    if (cat_lk && c->n_families && mode == CAFE_B200_GAMMA_LINSUM)
-        CUDA_TRY(c, cudaMemcpyAsync(cat_lk, c->d_cat_lk, (size_t)c->n_families * k * sizeof(double), cudaMemcpyDeviceToHost, s));
-    CUDA_TRY(c, cudaStreamSynchronize(s));
-    if (c->n_families == 0) { c->h_result[0] = 0.0; c->h_result[1] = 0.0; }
-    const int64_t nf = (int64_t)c->h_result[1];
+    for (Shard* s : c->shards) {
+        CUDA_TRY(c, cudaSetDevice(s->device));
+        cudaStream_t st = s->stream;
+        CUDA_TRY(c, cudaMemcpyAsync(s->h_result, s->d_result, 2 * sizeof(double), cudaMemcpyDeviceToHost, st));
+        if (family_lnl && s->n_families)
+            CUDA_TRY(c, cudaMemcpyAsync(family_lnl + s->first, s->d_family_lnl, (size_t)s->n_families * sizeof(double), cudaMemcpyDeviceToHost, st));
+        if (cat_lk && s->n_families && mode == CAFE_B200_GAMMA_LINSUM)
+            CUDA_TRY(c, cudaMemcpyAsync(cat_lk + (size_t)s->first * k, s->d_cat_lk, (size_t)s->n_families * k * sizeof(double), cudaMemcpyDeviceToHost, st));
+    }
+    rc = sync_all(c);
+    if (rc) return rc;
+    // the shards' pairs are added on the host in shard order: deterministic for a given device list
+    double sum = 0.0;
+    int64_t nf = 0;
+    for (Shard* s : c->shards) {
+        if (s->n_families == 0) continue;
+        sum += s->h_result[0];
+        nf += (int64_t)s->h_result[1];
+    }
     if (n_failed) *n_failed = nf;
-    *neg_lnl = nf > 0 ? INFINITY : -c->h_result[0];                       // src/gamma_core.cpp:227-236 / src/base_model.cpp:107
+    *neg_lnl = nf > 0 ? INFINITY : -sum;                                  // src/gamma_core.cpp:227-236 / src/base_model.cpp:107
     if (nf > 0 && failed_idx && failed_cap > 0) {
-        std::vector<uint8_t> flags((size_t)c->n_families);
-        CUDA_TRY(c, cudaMemcpy(flags.data(), c->d_family_fail, flags.size(), cudaMemcpyDeviceToHost));
         int64_t w = 0;
-        for (int64_t i = 0; i < c->n_families && w < failed_cap; ++i)
-            if (flags[i]) failed_idx[w++] = i;
+        for (Shard* s : c->shards) {
+            if (s->n_families == 0 || w >= failed_cap) continue;
+            std::vector<uint8_t> flags((size_t)s->n_families);
+            CUDA_TRY(c, cudaSetDevice(s->device));
+            CUDA_TRY(c, cudaMemcpy(flags.data(), s->d_family_fail, flags.size(), cudaMemcpyDeviceToHost));
+            for (int64_t i = 0; i < s->n_families && w < failed_cap; ++i)
+                if (flags[i]) failed_idx[w++] = s->first + i;
+        }
     }
     return CAFE_B200_OK;
+}
+
+int cafe_b200_fetch_category_likelihoods(cafe_b200_ctx* c, int k, double* cat_lk)
+{
+    if (!c || !cat_lk || k < 1 || k > c->cap_k) return fail(c, CAFE_B200_ERR_ARG, "bad argument to fetch_category_likelihoods");
+    for (Shard* s : c->shards) {
+        if (s->n_families == 0) continue;
+        CUDA_TRY(c, cudaSetDevice(s->device));
+        CUDA_TRY(c, cudaMemcpyAsync(cat_lk + (size_t)s->first * k, s->d_cat_lk, (size_t)s->n_families * k * sizeof(double), cudaMemcpyDeviceToHost, s->stream));
+    }
+    return sync_all(c);
 }
 
 int cafe_b200_matrix_size(const cafe_b200_ctx* c) { return c ? c->n : 0; }
@@ -930,23 +1043,24 @@ int cafe_b200_matrix_size(const cafe_b200_ctx* c) { return c ? c->n : 0; }
 int cafe_b200_build_matrices(cafe_b200_ctx* c, const double* lambdas, int n_lambdas, int k, double* out)
 {
     if (!c || !lambdas || !out || k < 1) return fail(c, CAFE_B200_ERR_ARG, "bad argument to build_matrices");
-    CUDA_TRY(c, cudaSetDevice(c->device));
     std::vector<double> ones(c->n, 1.0);
     int rc = stage_and_build(c, lambdas, n_lambdas, k, nullptr, ones.data(), c->n);
     if (rc) return rc;
     const HostTree& t = c->tree;
-    std::vector<int> mat_of((size_t)k * t.n_nodes);
+    Shard* s = c->shards[0];
+    CUDA_TRY(c, cudaSetDevice(s->device));
     std::vector<double> mt(c->mt_stride);
-    CUDA_TRY(c, cudaStreamSynchronize(c->stream));
-    CUDA_TRY(c, cudaMemcpy(mat_of.data(), c->d_mat_of, mat_of.size() * sizeof(int), cudaMemcpyDeviceToHost));
+    rc = sync_all(c);
+    if (rc) return rc;
+    const int* mat_of = reinterpret_cast<const int*>(c->h_param + c->lay.mat_of);
     const int cols = c->mf + 1;
     for (int cat = 0; cat < k; ++cat)
         for (int v = 0; v < t.n_nodes; ++v) {
             double* dst = out + ((size_t)cat * t.n_nodes + v) * c->n * cols;
             if (t.parent[v] < 0) { std::fill(dst, dst + (size_t)c->n * cols, 0.0); continue; }
-            CUDA_TRY(c, cudaMemcpy(mt.data(), c->d_mt + (size_t)mat_of[cat * t.n_nodes + v] * c->mt_stride, c->mt_stride * sizeof(double), cudaMemcpyDeviceToHost));
-            for (int s = 0; s < c->n; ++s)
-                for (int cc = 0; cc < cols; ++cc) dst[(size_t)s * cols + cc] = mt[(size_t)cc * c->nr + s];
+            CUDA_TRY(c, cudaMemcpy(mt.data(), s->d_mt + (size_t)mat_of[cat * t.n_nodes + v] * c->mt_stride, c->mt_stride * sizeof(double), cudaMemcpyDeviceToHost));
+            for (int sz = 0; sz < c->n; ++sz)
+                for (int cc = 0; cc < cols; ++cc) dst[(size_t)sz * cols + cc] = mt[(size_t)cc * c->nr + sz];
         }
     return CAFE_B200_OK;
 }
@@ -954,43 +1068,55 @@ int cafe_b200_build_matrices(cafe_b200_ctx* c, const double* lambdas, int n_lamb
 int cafe_b200_prune_roots(cafe_b200_ctx* c, const double* lambdas, int n_lambdas, int k, double* out)
 {
     if (!c || !lambdas || !out || k < 1) return fail(c, CAFE_B200_ERR_ARG, "bad argument to prune_roots");
-    CUDA_TRY(c, cudaSetDevice(c->device));
     int rc = check_counts(c);
     if (rc) return rc;
     std::vector<double> ones(c->n, 1.0), cp(k, 1.0);
     rc = stage_and_build(c, lambdas, n_lambdas, k, cp.data(), ones.data(), c->n);
     if (rc) return rc;
-    double* d_root = nullptr;
-    const size_t total = (size_t)c->n_families * k * c->mrf;
-    CUDA_TRY(c, dev_alloc(&d_root, total));
-    rc = launch_prune(c, k, CAFE_B200_GAMMA_LINSUM, d_root);
-    if (rc == CAFE_B200_OK) {
-        cudaError_t e = cudaEventRecord(c->ev[2], c->stream);
-        if (e == cudaSuccess) e = cudaStreamSynchronize(c->stream);
-        if (e == cudaSuccess) e = cudaMemcpy(out, d_root, total * sizeof(double), cudaMemcpyDeviceToHost);
-        if (e != cudaSuccess) rc = fail(c, CAFE_B200_ERR_CUDA, cudaGetErrorString(e));
-        c->ev_valid[2] = true; c->ev_valid[3] = c->ev_valid[4] = false;
+    std::vector<double*> d_root(c->shards.size(), nullptr);
+    for (size_t i = 0; i < c->shards.size() && rc == CAFE_B200_OK; ++i) {
+        Shard* s = c->shards[i];
+        const size_t total = (size_t)s->n_families * k * c->mrf;
+        cudaError_t e = cudaSetDevice(s->device);
+        if (e == cudaSuccess) e = dev_alloc(&d_root[i], total);
+        if (e != cudaSuccess) { rc = fail(c, CAFE_B200_ERR_CUDA, cudaGetErrorString(e)); break; }
+        rc = launch_prune(c, s, k, CAFE_B200_GAMMA_LINSUM, d_root[i]);
+        if (rc == CAFE_B200_OK) {
+            e = cudaEventRecord(s->ev[2], s->stream);
+            if (e == cudaSuccess) e = cudaMemcpyAsync(out + (size_t)s->first * k * c->mrf, d_root[i], total * sizeof(double), cudaMemcpyDeviceToHost, s->stream);
+            if (e != cudaSuccess) rc = fail(c, CAFE_B200_ERR_CUDA, cudaGetErrorString(e));
+            s->ev_valid[2] = true; s->ev_valid[3] = s->ev_valid[4] = false;
+        }
     }
-    cudaFree(d_root);
-    return rc;
+    const int rc2 = sync_all(c);
+    for (size_t i = 0; i < c->shards.size(); ++i) {
+        cudaSetDevice(c->shards[i]->device);
+        cudaFree(d_root[i]);
+    }
+    return rc ? rc : rc2;
 }
 
 int cafe_b200_root_max(cafe_b200_ctx* c, const double* lambdas, int n_lambdas, double* out)
 {
     if (!c || !lambdas || !out) return fail(c, CAFE_B200_ERR_ARG, "bad argument to root_max");
-    CUDA_TRY(c, cudaSetDevice(c->device));
+    NvtxRange r("cafe_b200_root_max");
     int rc = check_counts(c);
     if (rc) return rc;
     std::vector<double> ones(c->n, 1.0);
     const double cp = 1.0;
     rc = stage_and_build(c, lambdas, n_lambdas, 1, &cp, ones.data(), c->n);
     if (rc) return rc;
-    rc = launch_prune(c, 1, CAFE_B200_ROOT_MAX, nullptr);
+    for (Shard* s : c->shards) {
+        CUDA_TRY(c, cudaSetDevice(s->device));
+        rc = launch_prune(c, s, 1, CAFE_B200_ROOT_MAX, nullptr);
+        if (rc) return rc;
+        CUDA_TRY(c, cudaEventRecord(s->ev[2], s->stream));
+        s->ev_valid[2] = true; s->ev_valid[3] = s->ev_valid[4] = false;
+        if (s->n_families)
+            CUDA_TRY(c, cudaMemcpyAsync(out + s->first, s->d_cat_lk, (size_t)s->n_families * sizeof(double), cudaMemcpyDeviceToHost, s->stream));
+    }
+    rc = sync_all(c);
     if (rc) return rc;
-    CUDA_TRY(c, cudaEventRecord(c->ev[2], c->stream));
-    c->ev_valid[2] = true; c->ev_valid[3] = c->ev_valid[4] = false;
-    CUDA_TRY(c, cudaMemcpyAsync(out, c->d_cat_lk, (size_t)c->n_families * sizeof(double), cudaMemcpyDeviceToHost, c->stream));
-    CUDA_TRY(c, cudaStreamSynchronize(c->stream));
     c->evals++;
     return CAFE_B200_OK;
 }
@@ -1033,35 +1159,48 @@ int cafe_b200_branch_probabilities(cafe_b200_ctx* c, const double* lambdas, int 
 {
     if (!c || !lambdas || !node_sizes || !out) return fail(c, CAFE_B200_ERR_ARG, "bad argument to branch_probabilities");
     if (c->n_families == 0) return CAFE_B200_OK;
+    NvtxRange r("cafe_b200_branch_probabilities");
     const int nn = c->tree.n_nodes;
-    const size_t total = (size_t)c->n_families * nn;
+    const size_t total_all = (size_t)c->n_families * nn;
     const int hi = std::min(c->mf, c->n - 1);
-    for (size_t i = 0; i < total; ++i)
+    for (size_t i = 0; i < total_all; ++i)
         if (node_sizes[i] < 0 || node_sizes[i] > hi) return fail(c, CAFE_B200_ERR_COUNT_RANGE, "a node size is outside 0..max_family_size");
-    CUDA_TRY(c, cudaSetDevice(c->device));
     std::vector<double> ones(c->n, 1.0);
     const double cp = 1.0;
     int rc = stage_and_build(c, lambdas, n_lambdas, 1, &cp, ones.data(), c->n);
     if (rc) return rc;
-    int32_t* d_sizes = nullptr;
-    uint8_t* d_sel = nullptr;
-    double* d_out = nullptr;
-    cudaError_t e = dev_alloc(&d_sizes, total);
-    if (e == cudaSuccess) e = dev_alloc(&d_out, total);
-    if (e == cudaSuccess && selected) e = dev_alloc(&d_sel, (size_t)c->n_families);
-    if (e == cudaSuccess) e = cudaMemcpyAsync(d_sizes, node_sizes, total * sizeof(int32_t), cudaMemcpyHostToDevice, c->stream);
-    if (e == cudaSuccess && selected) e = cudaMemcpyAsync(d_sel, selected, (size_t)c->n_families, cudaMemcpyHostToDevice, c->stream);
-    if (e == cudaSuccess) {
-        const int blocks = (int)((total + VT_THREADS - 1) / VT_THREADS);
-        viterbi_kernel<<<blocks, VT_THREADS, 0, c->stream>>>(c->n_families, nn, c->mf, c->nr, c->d_parent, c->d_mat_of, c->d_mt, c->mt_stride, d_sizes,
-                                                              d_sel, d_out);
-        e = cudaGetLastError();
-        c->launches++;
+    const size_t ns = c->shards.size();
+    std::vector<int32_t*> d_sizes(ns, nullptr);
+    std::vector<uint8_t*> d_sel(ns, nullptr);
+    std::vector<double*> d_out(ns, nullptr);
+    cudaError_t e = cudaSuccess;
+    for (size_t i = 0; i < ns && e == cudaSuccess; ++i) {
+        Shard* s = c->shards[i];
+        if (s->n_families == 0) continue;
+        const size_t total = (size_t)s->n_families * nn;
+        e = cudaSetDevice(s->device);
+        if (e == cudaSuccess) e = dev_alloc(&d_sizes[i], total);
+        if (e == cudaSuccess) e = dev_alloc(&d_out[i], total);
+        if (e == cudaSuccess && selected) e = dev_alloc(&d_sel[i], (size_t)s->n_families);
+        if (e == cudaSuccess) e = cudaMemcpyAsync(d_sizes[i], node_sizes + (size_t)s->first * nn, total * sizeof(int32_t), cudaMemcpyHostToDevice, s->stream);
+        if (e == cudaSuccess && selected) e = cudaMemcpyAsync(d_sel[i], selected + s->first, (size_t)s->n_families, cudaMemcpyHostToDevice, s->stream);
+        if (e == cudaSuccess) {
+            const int blocks = (int)((total + VT_THREADS - 1) / VT_THREADS);
+            viterbi_kernel<<<blocks, VT_THREADS, 0, s->stream>>>(s->n_families, nn, c->mf, c->nr, s->d_parent,
+                                                                  reinterpret_cast<const int*>(s->d_param + c->lay.mat_of), s->d_mt, c->mt_stride,
+                                                                  d_sizes[i], d_sel[i], d_out[i]);
+            e = cudaGetLastError();
+            c->launches++;
+        }
+        if (e == cudaSuccess) e = cudaMemcpyAsync(out + (size_t)s->first * nn, d_out[i], total * sizeof(double), cudaMemcpyDeviceToHost, s->stream);
     }
-    if (e == cudaSuccess) e = cudaMemcpyAsync(out, d_out, total * sizeof(double), cudaMemcpyDeviceToHost, c->stream);
-    if (e == cudaSuccess) e = cudaStreamSynchronize(c->stream);
-    cudaStreamSynchronize(c->stream);
-    cudaFree(d_sizes); cudaFree(d_sel); cudaFree(d_out);
+    for (size_t i = 0; i < ns; ++i) {
+        Shard* s = c->shards[i];
+        cudaSetDevice(s->device);
+        cudaError_t e2 = cudaStreamSynchronize(s->stream);
+        if (e == cudaSuccess) e = e2;
+        cudaFree(d_sizes[i]); cudaFree(d_sel[i]); cudaFree(d_out[i]);
+    }
     if (e != cudaSuccess) return fail(c, CAFE_B200_ERR_CUDA, std::string("branch_probabilities: ") + cudaGetErrorString(e));
     return CAFE_B200_OK;
 }
@@ -1069,17 +1208,25 @@ int cafe_b200_branch_probabilities(cafe_b200_ctx* c, const double* lambdas, int 
 int cafe_b200_reconstruct(cafe_b200_ctx* c, const double* lambdas, int n_lambdas, int k, const double* prior_by_size, int32_t* states)
 {
     if (!c || !lambdas || !prior_by_size || !states || k < 1) return fail(c, CAFE_B200_ERR_ARG, "bad argument to reconstruct");
-    CUDA_TRY(c, cudaSetDevice(c->device));
+    if (c->hw_slots < 2) return fail(c, CAFE_B200_ERR_LIMIT, "reconstruction supports matrix sizes up to 256");
+    NvtxRange r("cafe_b200_reconstruct");
     int rc = check_counts(c);
     if (rc) return rc;
     const int lim = std::min(c->mf, c->mrf) + 1;
     rc = stage_and_build(c, lambdas, n_lambdas, k, nullptr, prior_by_size, lim);
     if (rc) return rc;
-    rc = launch_pupko(c, k, states);
-    if (rc) return rc;
-    c->ev_valid[2] = c->ev_valid[3] = false;
-    c->ev_valid[4] = true;
-    return CAFE_B200_OK;
+    for (Shard* s : c->shards) {
+        CUDA_TRY(c, cudaSetDevice(s->device));
+        rc = launch_pupko(c, s, k);
+        if (rc) return rc;
+        if (s->n_families == 0) continue;
+        CUDA_TRY(c, cudaEventRecord(s->ev[4], s->stream));
+        const size_t n_states = (size_t)s->n_families * k * c->tree.n_internal;
+        CUDA_TRY(c, cudaMemcpyAsync(states + (size_t)s->first * k * c->tree.n_internal, s->d_states, n_states * sizeof(int32_t), cudaMemcpyDeviceToHost, s->stream));
+        s->ev_valid[2] = s->ev_valid[3] = false;
+        s->ev_valid[4] = true;
+    }
+    return sync_all(c);
 }
 
 int64_t cafe_b200_launch_count(const cafe_b200_ctx* c) { return c ? c->launches : 0; }
@@ -1088,12 +1235,25 @@ int cafe_b200_last_timings(const cafe_b200_ctx* c, double* ms4)
 {
     if (!c || !ms4) return CAFE_B200_ERR_ARG;
     for (int i = 0; i < 4; ++i) ms4[i] = 0.0;
-    float ms = 0.f;
-    if (c->ev_valid[0] && c->ev_valid[1] && cudaEventElapsedTime(&ms, c->ev[0], c->ev[1]) == cudaSuccess) ms4[0] = ms;
-    if (c->ev_valid[1] && c->ev_valid[2] && cudaEventElapsedTime(&ms, c->ev[1], c->ev[2]) == cudaSuccess) ms4[1] = ms;
-    if (c->ev_valid[2] && c->ev_valid[3] && cudaEventElapsedTime(&ms, c->ev[2], c->ev[3]) == cudaSuccess) ms4[2] = ms;
-    if (c->ev_valid[1] && c->ev_valid[4] && cudaEventElapsedTime(&ms, c->ev[1], c->ev[4]) == cudaSuccess) ms4[3] = ms;
-    cudaGetLastError();
+    for (const Shard* s : c->shards) {
+        float ms = 0.f;
+        if (s->ev_valid[0] && s->ev_valid[1] && cudaEventElapsedTime(&ms, s->ev[0], s->ev[1]) == cudaSuccess) ms4[0] = std::max(ms4[0], (double)ms);
+        if (s->ev_valid[1] && s->ev_valid[2] && cudaEventElapsedTime(&ms, s->ev[1], s->ev[2]) == cudaSuccess) ms4[1] = std::max(ms4[1], (double)ms);
+        if (s->ev_valid[2] && s->ev_valid[3] && cudaEventElapsedTime(&ms, s->ev[2], s->ev[3]) == cudaSuccess) ms4[2] = std::max(ms4[2], (double)ms);
+        if (s->ev_valid[1] && s->ev_valid[4] && cudaEventElapsedTime(&ms, s->ev[1], s->ev[4]) == cudaSuccess) ms4[3] = std::max(ms4[3], (double)ms);
+        cudaGetLastError();
+    }
+    return CAFE_B200_OK;
+}
+
+int cafe_b200_describe(const cafe_b200_ctx* c, char* out, int cap)
+{
+    if (!c || !out || cap < 1) return CAFE_B200_ERR_ARG;
+    snprintf(out, cap,
+             "devices=%zu matrix=%d rows=%d geom(rb=%d,gw=%d,groups=%d,cps=%d,producers=%d) stages=%d smem=%d count_bytes=%d counts_in_smem=%d "
+             "program_in_smem=%d stack_depth=%d tmem_entries=%d tmem_cols=%d spill_entries=%d gemm_ops=%d ops=%zu",
+             c->shards.size(), c->n, c->nr, c->geom.rb, c->geom.gw, c->geom.ng, c->geom.cps, c->geom.pw, c->n_stages, c->prune_smem, c->cnt_width,
+             c->cnt_smem_bytes > 0 ? 1 : 0, c->ops_smem_bytes > 0 ? 1 : 0, c->prog.depth, c->tmem_entries, c->tmem_cols, c->n_gspill, c->prog.n_gemm, c->prog.ops.size());
     return CAFE_B200_OK;
 }
 

@@ -27,7 +27,7 @@ __host__ __device__ constexpr int nr_of(int mb) { return 32 * mb; }
 __host__ __device__ constexpr int ldv_of(int mb) { return 32 * mb + 4; }            // stride % 16 == 4 (8-byte words)
 __host__ __device__ constexpr int stage_doubles(int mb) { return PPS * 4 * 32 * mb; }
 
-// Schedule op codes (host-built, one list per tree; see build_schedule in cafe_b200.cu)
+// Slot-machine op codes of the reconstruction kernel's schedule (host-built, one list per tree; ScheduleBuilder in cafe_b200.cu)
 enum : int {
     OP_LEAF_SET = 0,   // V[a] = column obs of M(node)            (leaf child, first factor of its parent)
     OP_LEAF_MUL = 1,   // V[a] *= column obs of M(node)
@@ -35,15 +35,11 @@ enum : int {
     OP_GEMM_MUL = 3,   // V[a] *= M(node) * V[b]
     OP_SPILL = 4,      // scratch[b] = V[a]
     OP_FILL = 5,       // V[a] = scratch[b]
-    OP_RESCALE = 6,    // per-family power-of-two renormalisation of V[a]
-    OP_ROOT = 7,       // root prior / category weight, write results
-    // fused forms (pruning kernel only, no error model): same arithmetic, fewer passes over shared memory
-    OP_LEAF_SET2 = 8,      // V[a] = column(leaf node) * column(leaf node2)             (a cherry in one pass)
-    OP_GEMM_SET_LEAF = 9,  // V[a] = (M(node) * V[a]) * column(leaf node2)              (leaf sibling folded into the epilogue)
-    OP_GEMM_MUL_LEAF = 10  // V[a] *= (M(node) * V[b]) * column(leaf node2)
+    OP_RESCALE = 6,    // (unused by the kernels; marks the end of an internal node)
+    OP_ROOT = 7        // root prior, write results
 };
 
-// Tree-level op as the host schedule builder emits it (also what the reconstruction kernel walks).
+// Tree-level op as the host schedule builder emits it (what the reconstruction kernel walks).
 struct Op {
     int type;
     int a;
@@ -51,16 +47,26 @@ struct Op {
     int node;
 };
 
+// Stack-machine program of the pruning kernel (ProgramBuilder in cafe_b200.cu; semantics in prune.cuh).
+enum : int { POP_LEAVES = 0, POP_GEMM = 1, POP_ROOT = 2 };
+constexpr int PF_PARKED = 1;   // GEMM: multiply by the partial product parked at `park` (pop)
+constexpr int PF_PARK = 2;     // GEMM: park the result at `park` (push) instead of completing the parent's vector
+
 // Pruning op with everything resolved for one rate category: one aligned 32-byte load per op.
 struct __align__(16) POp {
     int type;
-    int a;
-    int b;
+    int mat;         // GEMM: unique-matrix slot of the child's edge
+    int flags;
+    int park;        // stack entry: >= 0 tensor-memory entry, < 0: -(device scratch entry + 1)
+    int leaf_begin;  // this op's leaf list in the per-category LeafRef array: n_pre entries, then n_post
+    int n_pre;       // GEMM: leaves multiplied before the GEMM factor (n-ary nodes, Newick order); LEAVES: all of them
+    int n_post;      // GEMM: leaves multiplied after it
     int node;
-    int mat;     // unique-matrix slot of `node`
-    int col;     // count column of `node` when it is a leaf
-    int mat2;    // fused leaf sibling: matrix slot
-    int col2;    //                     count column
+};
+
+struct LeafRef {
+    int mat;         // unique-matrix slot of the leaf's edge
+    int col;         // its column of the count matrix
 };
 
 struct PruneParams {
@@ -72,20 +78,26 @@ struct PruneParams {
     int mf;                 // max_family_size
     int mrf;                // max_root_family_size
     int n_ops;
+    int n_leafrefs;
     int n_kchunks;          // K chunks per GEMM (each PPS*4 columns)
     int mode;
     int rescale;
-    int n_spill;            // scratch vectors per block
     int err_rows;
     int err_ndev;
     int counts_in_smem;
-    int n_slots;
-    int n_stages;           // ring depth (power of two)
-    int stage_shift;        // log2(n_stages)
+    int cnt_smem_bytes;     // staged leaf counts of one tile (0 when they do not fit)
+    int cnt_width;          // bytes per leaf count on the device: 1 (max_family_size <= 255) or 2
+    int ops_in_smem;        // the per-category program is staged in shared memory
+    int n_stages;           // ring depth
+    int depth;              // parked-stack depth of the program
+    int n_gspill;           // ... of which the outermost entries live in device scratch
+    int tmem_entries;       // ... and the rest in tensor memory (entries per warp)
+    int tmem_cols;          // tensor-memory columns to allocate (power of two >= 32, 0 = none)
     int64_t n_tiles;        // tiles of (groups x 16) families = work items per category
     // device pointers
     const POp* ops;                 // [k][n_ops]
-    const int32_t* counts;          // [F][n_leaves]
+    const LeafRef* leaves;          // [k][n_leafrefs]
+    const void* counts;             // [F padded to whole tiles][n_leaves] uint8 (max_family_size <= 255) or uint16
     const double* mp;               // panelised matrices   [U][kpanels][NR][4]
     const double* mt;               // transposed matrices  [U][mf+1][NR]
     size_t mp_stride;               // doubles per matrix
@@ -94,8 +106,7 @@ struct PruneParams {
     const double* prior;            // [mrf]
     const double* logprior;         // [mrf]
     const double* cat_probs;        // [k]
-    double* scratch;                // [grid][n_spill][FT*LDV]
-    int* scratch_exp;               // [grid][n_spill][FT]
+    double* scratch;                // [grid][n_gspill][4*RB][consumer threads]
     // outputs
     double* cat_lk;                 // [F][k]   (gamma)  or family lnL [F] (base)
     uint8_t* fail;                  // [F][k]
@@ -140,6 +151,42 @@ __device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity)
         "}\n" ::"r"(smem_u32(bar)),
         "r"(parity)
         : "memory");
+}
+
+// The same on 32-bit shared addresses (the K loop keeps them in registers instead of re-deriving them from pointers).
+__device__ __forceinline__ void mbar_wait_u32(uint32_t bar, uint32_t parity)
+{
+    asm volatile(
+        "{\n"
+        ".reg .pred p;\n"
+        "WAIT_LOOP_U:\n"
+        "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n"
+        "@p bra WAIT_DONE_U;\n"
+        "bra WAIT_LOOP_U;\n"
+        "WAIT_DONE_U:\n"
+        "}\n" ::"r"(bar),
+        "r"(parity)
+        : "memory");
+}
+
+__device__ __forceinline__ void mbar_arrive_u32(uint32_t bar)
+{
+    asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(bar) : "memory");
+}
+
+// Opaque copy: the value lives in a register from here on (no rematerialisation from its inputs).
+__device__ __forceinline__ uint32_t pin_u32(uint32_t x)
+{
+    uint32_t y;
+    asm volatile("mov.u32 %0, %1;" : "=r"(y) : "r"(x));
+    return y;
+}
+
+__device__ __forceinline__ double lds_f64(uint32_t addr)
+{
+    double v;
+    asm volatile("ld.shared.f64 %0, [%1];" : "=d"(v) : "r"(addr));
+    return v;
 }
 
 // 1-D bulk copy global -> shared through the TMA engine; completion is signalled on the mbarrier.

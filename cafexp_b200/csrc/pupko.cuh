@@ -34,9 +34,10 @@ struct PupkoParams {
     int n_spill;
     int n_slots;
     int counts_in_smem;
+    int cnt_width;                  // bytes per leaf count: 1 or 2
     int64_t n_tiles;
     const Op* ops;
-    const int32_t* counts;
+    const void* counts;
     const int* leaf_col;
     const int* parent;
     const int* internal_idx;        // [n_nodes] position among internal nodes, -1 for leaves
@@ -45,7 +46,8 @@ struct PupkoParams {
     size_t mt_stride;
     const double* prior;            // indexed by root size
     double* scratch;                // [grid][n_spill][FT*LDV]
-    uint8_t* ctab;                  // [grid][n_nodes][FT][NR] argmax tables of the current tile
+    uint8_t* ctab;                  // [grid][n_internal][FT][NR] argmax tables of the current tile (indexed by internal node:
+                                    // half the footprint of a per-node table, so 148 tiles in flight stay L2-resident)
     int32_t* states;                // [F][k][n_internal]
 };
 
@@ -115,7 +117,10 @@ __global__ void __launch_bounds__(PRUNE_THREADS, 1) pupko_kernel(const PupkoPara
     }
 
     uint32_t pos = 0;
-    uint8_t* ctab = p.ctab + (size_t)blockIdx.x * p.n_nodes * FT * NR;
+    uint8_t* ctab = p.ctab + (size_t)blockIdx.x * p.n_internal * FT * NR;
+    auto count_at = [&](int64_t i) -> int {
+        return p.cnt_width == 1 ? (int)reinterpret_cast<const uint8_t*>(p.counts)[i] : (int)reinterpret_cast<const uint16_t*>(p.counts)[i];
+    };
 
     for (int64_t item = blockIdx.x; item < n_items; item += gridDim.x) {
         const int cat = (int)(item / p.n_tiles);
@@ -129,7 +134,7 @@ __global__ void __launch_bounds__(PRUNE_THREADS, 1) pupko_kernel(const PupkoPara
                 const int f = i / p.n_leaves;
                 int64_t fam = fam0 + f;
                 if (fam >= p.n_families) fam = p.n_families - 1;
-                cnt_s[i] = (uint16_t)p.counts[fam * p.n_leaves + (i - f * p.n_leaves)];
+                cnt_s[i] = (uint16_t)count_at(fam * p.n_leaves + (i - f * p.n_leaves));
             }
         }
         consumer_sync();
@@ -150,7 +155,7 @@ __global__ void __launch_bounds__(PRUNE_THREADS, 1) pupko_kernel(const PupkoPara
                     else {
                         int64_t fam = fam0 + f;
                         if (fam >= p.n_families) fam = p.n_families - 1;
-                        obs = p.counts[fam * p.n_leaves + col];
+                        obs = count_at(fam * p.n_leaves + col);
                     }
                     const double* src = mt + (size_t)obs * NR;
                     double* row = dst + (size_t)f * LDV;
@@ -203,7 +208,7 @@ __global__ void __launch_bounds__(PRUNE_THREADS, 1) pupko_kernel(const PupkoPara
                 }
                 consumer_sync();
                 double* dst = slots + (size_t)op.a * L::SLOT_DOUBLES;
-                uint8_t* ct = ctab + (size_t)op.node * FT * NR;
+                uint8_t* ct = ctab + (size_t)p.internal_idx[op.node] * FT * NR;
                 #pragma unroll
                 for (int fi = 0; fi < FPW; ++fi) {
                     const int f = warp * FPW + fi;
@@ -249,7 +254,7 @@ __global__ void __launch_bounds__(PRUNE_THREADS, 1) pupko_kernel(const PupkoPara
                         const int ii = p.internal_idx[v];
                         if (ii < 0) continue;
                         const int ps = out[p.internal_idx[p.parent[v]]];
-                        out[ii] = ctab[((size_t)v * FT + f) * NR + ps];
+                        out[ii] = ctab[((size_t)ii * FT + f) * NR + ps];
                     }
                 }
                 break;

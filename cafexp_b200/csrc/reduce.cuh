@@ -78,22 +78,27 @@ __global__ void __launch_bounds__(RED_THREADS) final_sum_kernel(int n_partials, 
     if (threadIdx.x == 0) { result[0] = s_sum[0]; result[1] = s_bad[0]; }
 }
 
-// Range check of an uploaded count matrix (cafe_b200_set_families): range[0] = min, range[1] = max over all
-// leaf counts, so that the reference's out-of-range indexing (src/probability.cpp:191,197) is refused without a
-// host pass over the matrix.  Bound: HBM — 4 B per count, 16-byte vector loads, grid-stride.
-__global__ void __launch_bounds__(RED_THREADS) count_range_kernel(const int32_t* __restrict__ counts, int64_t n, int* __restrict__ range)
+// Ingest of an uploaded count matrix (cafe_b200_set_families): narrow the caller's elements (1, 2 or 4 bytes) to the
+// device width (1 byte when max_family_size <= 255, else 2) and track range[0] = min, range[1] = max over all leaf
+// counts in the same pass, so that the reference's out-of-range indexing (src/probability.cpp:191,197) is refused
+// without a host pass over the matrix.  Out-of-range values are stored as 0 (the context refuses to evaluate them).
+// Bound: HBM — one read and one write per count, grid-stride.
+__global__ void __launch_bounds__(RED_THREADS) ingest_counts_kernel(const void* src, int src_bytes, void* dst, int dst_bytes,
+                                                                    int64_t n, int mf, int* __restrict__ range)
 {
     int lo = INT_MAX, hi = INT_MIN;
-    const int64_t n4 = n / 4;
-    const int4* c4 = reinterpret_cast<const int4*>(counts);
-    for (int64_t i = (int64_t)blockIdx.x * RED_THREADS + threadIdx.x; i < n4; i += (int64_t)gridDim.x * RED_THREADS) {
-        const int4 v = __ldg(c4 + i);
-        lo = min(lo, min(min(v.x, v.y), min(v.z, v.w)));
-        hi = max(hi, max(max(v.x, v.y), max(v.z, v.w)));
-    }
-    for (int64_t i = n4 * 4 + (int64_t)blockIdx.x * RED_THREADS + threadIdx.x; i < n; i += (int64_t)gridDim.x * RED_THREADS) {
-        lo = min(lo, counts[i]);
-        hi = max(hi, counts[i]);
+    for (int64_t i = (int64_t)blockIdx.x * RED_THREADS + threadIdx.x; i < n; i += (int64_t)gridDim.x * RED_THREADS) {
+        int v;
+        if (src_bytes == 4) v = reinterpret_cast<const int32_t*>(src)[i];
+        else if (src_bytes == 2) v = reinterpret_cast<const uint16_t*>(src)[i];
+        else v = reinterpret_cast<const uint8_t*>(src)[i];
+        lo = min(lo, v);
+        hi = max(hi, v);
+        if (src != dst || src_bytes != dst_bytes) {
+            const int w = (v < 0 || v > mf) ? 0 : v;
+            if (dst_bytes == 1) reinterpret_cast<uint8_t*>(dst)[i] = (uint8_t)w;
+            else reinterpret_cast<uint16_t*>(dst)[i] = (uint16_t)w;
+        }
     }
     #pragma unroll
     for (int off = 16; off > 0; off >>= 1) {

@@ -29,7 +29,8 @@ EXPORTS = [
     "cafe_b200_last_error", "cafe_b200_set_families", "cafe_b200_set_error_model", "cafe_b200_set_option", "cafe_b200_set_stream",
     "cafe_b200_eval", "cafe_b200_eval_device", "cafe_b200_reconstruct", "cafe_b200_build_matrices", "cafe_b200_matrix_size",
     "cafe_b200_prune_roots", "cafe_b200_launch_count", "cafe_b200_last_timings", "cafe_b200_root_max", "cafe_b200_pvalues",
-    "cafe_b200_branch_probabilities",
+    "cafe_b200_branch_probabilities", "cafe_b200_create_multi", "cafe_b200_n_devices", "cafe_b200_alloc_pinned", "cafe_b200_free_pinned",
+    "cafe_b200_set_families_ex", "cafe_b200_plan_program", "cafe_b200_describe", "cafe_b200_fetch_category_likelihoods",
 ]
 
 _dp = C.POINTER(C.c_double)
@@ -68,6 +69,22 @@ def load_library():
     L.cafe_b200_device_count.restype = C.c_int
     L.cafe_b200_create.restype = C.c_int
     L.cafe_b200_create.argtypes = [C.POINTER(C.c_void_p), C.POINTER(_Tree), _i32p, C.c_int64, C.c_int, C.c_int, C.c_int, C.c_int]
+    L.cafe_b200_create_multi.restype = C.c_int
+    L.cafe_b200_create_multi.argtypes = [C.POINTER(C.c_void_p), C.POINTER(_Tree), C.c_void_p, C.c_int, C.c_int64, C.c_int, C.c_int, C.c_int,
+                                         _ip, C.c_int]
+    L.cafe_b200_n_devices.restype = C.c_int
+    L.cafe_b200_n_devices.argtypes = [C.c_void_p]
+    L.cafe_b200_alloc_pinned.restype = C.c_void_p
+    L.cafe_b200_alloc_pinned.argtypes = [C.c_size_t]
+    L.cafe_b200_free_pinned.argtypes = [C.c_void_p]
+    L.cafe_b200_set_families_ex.restype = C.c_int
+    L.cafe_b200_set_families_ex.argtypes = [C.c_void_p, C.c_void_p, C.c_int, C.c_int64]
+    L.cafe_b200_plan_program.restype = C.c_int
+    L.cafe_b200_plan_program.argtypes = [C.POINTER(_Tree), _ip, C.c_int, _ip, _ip, C.c_int, _ip, _ip]
+    L.cafe_b200_fetch_category_likelihoods.restype = C.c_int
+    L.cafe_b200_fetch_category_likelihoods.argtypes = [C.c_void_p, C.c_int, _dp]
+    L.cafe_b200_describe.restype = C.c_int
+    L.cafe_b200_describe.argtypes = [C.c_void_p, C.c_char_p, C.c_int]
     L.cafe_b200_destroy.argtypes = [C.c_void_p]
     L.cafe_b200_last_error.restype = C.c_char_p
     L.cafe_b200_last_error.argtypes = [C.c_void_p]
@@ -101,7 +118,7 @@ def load_library():
     L.cafe_b200_launch_count.argtypes = [C.c_void_p]
     L.cafe_b200_last_timings.restype = C.c_int
     L.cafe_b200_last_timings.argtypes = [C.c_void_p, _dp]
-    if L.cafe_b200_abi_version() != 1:
+    if L.cafe_b200_abi_version() != 2:
         raise CafeB200Error("libcafe_b200.so ABI version mismatch")
     _lib = L
     return L
@@ -121,21 +138,36 @@ def _d(a):
     return a.ctypes.data_as(_dp)
 
 
-class Engine:
-    """One context = one (tree, family shard, size limits) on one GPU; mirrors what a reference
-    ``model`` object holds between evaluations (src/core.h:122-186)."""
+def tree_struct(tree):
+    """(ctypes struct, arrays it points into) for a flattened tree."""
+    arrays = [np.ascontiguousarray(tree.parent, np.int32), np.ascontiguousarray(tree.child_offset, np.int32),
+              np.ascontiguousarray(tree.child_list, np.int32), np.ascontiguousarray(tree.leaf_col, np.int32),
+              np.ascontiguousarray(tree.branch, np.float64), np.ascontiguousarray(tree.lambda_index, np.int32)]
+    a = arrays
+    ts = _Tree(len(a[0]), a[0].ctypes.data_as(_ip), a[1].ctypes.data_as(_ip), a[2].ctypes.data_as(_ip), a[3].ctypes.data_as(_ip),
+               _d(a[4]), a[5].ctypes.data_as(_ip))
+    return ts, arrays
 
-    def __init__(self, tree, counts: np.ndarray, max_family_size: int, max_root_family_size: int, device: int = 0):
+
+def _count_array(counts: np.ndarray) -> np.ndarray:
+    """Counts as the ABI takes them: uint8 / uint16 stay as they are (a quarter / half of the bytes on the wire),
+    everything else becomes int32."""
+    counts = np.asarray(counts)
+    if counts.dtype in (np.uint8, np.uint16, np.int32):
+        return np.ascontiguousarray(counts)
+    return np.ascontiguousarray(counts, np.int32)
+
+
+class Engine:
+    """One context = one (tree, families, size limits) on one GPU or — ``device`` a list — sharded over several GPUs of
+    the box; mirrors what a reference ``model`` object holds between evaluations (src/core.h:122-186)."""
+
+    def __init__(self, tree, counts: np.ndarray, max_family_size: int, max_root_family_size: int, device=0):
         L = load_library()
         self._lib = L
         self.tree = tree
-        self._arrays = [np.ascontiguousarray(tree.parent, np.int32), np.ascontiguousarray(tree.child_offset, np.int32),
-                        np.ascontiguousarray(tree.child_list, np.int32), np.ascontiguousarray(tree.leaf_col, np.int32),
-                        np.ascontiguousarray(tree.branch, np.float64), np.ascontiguousarray(tree.lambda_index, np.int32)]
-        a = self._arrays
-        ts = _Tree(len(a[0]), a[0].ctypes.data_as(_ip), a[1].ctypes.data_as(_ip), a[2].ctypes.data_as(_ip), a[3].ctypes.data_as(_ip),
-                   _d(a[4]), a[5].ctypes.data_as(_ip))
-        counts = np.ascontiguousarray(counts, np.int32)
+        ts, self._arrays = tree_struct(tree)
+        counts = _count_array(counts)
         if counts.ndim != 2 or counts.shape[1] != tree.n_leaves:
             raise ValueError("counts must be [n_families, n_leaves]")
         self.n_families = int(counts.shape[0])
@@ -143,14 +175,21 @@ class Engine:
         self.n_internal = int((np.asarray(tree.leaf_col) < 0).sum())
         self.mf = int(max_family_size)
         self.mrf = int(max_root_family_size)
-        self.device = device
+        self.devices = [int(d) for d in (device if isinstance(device, (list, tuple)) else [device])]
+        self.device = self.devices[0]
+        devs = np.ascontiguousarray(self.devices, np.int32)
         handle = C.c_void_p()
-        rc = L.cafe_b200_create(C.byref(handle), C.byref(ts), counts.ctypes.data_as(_i32p), self.n_families, self.n_leaves,
-                                self.mf, self.mrf, device)
+        rc = L.cafe_b200_create_multi(C.byref(handle), C.byref(ts), counts.ctypes.data_as(C.c_void_p), counts.dtype.itemsize, self.n_families,
+                                      self.n_leaves, self.mf, self.mrf, devs.ctypes.data_as(_ip), len(self.devices))
         if rc != 0:
             raise CafeB200Error(f"cafe_b200_create: {ERR_NAMES.get(rc, rc)}: {L.cafe_b200_last_error(None).decode()}")
         self._h = handle
         self.matrix_size = L.cafe_b200_matrix_size(self._h)
+
+    def describe(self) -> str:
+        buf = C.create_string_buffer(1024)
+        self._lib.cafe_b200_describe(self._h, buf, 1024)
+        return buf.value.decode()
 
     # -- lifetime -------------------------------------------------------------------------------
     def close(self):
@@ -176,8 +215,9 @@ class Engine:
 
     # -- configuration --------------------------------------------------------------------------
     def set_families(self, counts: np.ndarray):
-        counts = np.ascontiguousarray(counts, np.int32)
-        self._check(self._lib.cafe_b200_set_families(self._h, counts.ctypes.data_as(_i32p), counts.shape[0]), "set_families")
+        counts = _count_array(counts)
+        self._check(self._lib.cafe_b200_set_families_ex(self._h, counts.ctypes.data_as(C.c_void_p), counts.dtype.itemsize, counts.shape[0]),
+                    "set_families")
 
     def set_error_model(self, table: Optional[np.ndarray]):
         if table is None:
@@ -190,7 +230,7 @@ class Engine:
         self._check(self._lib.cafe_b200_set_option(self._h, OPT_RESCALE, 1 if on else 0), "set_option")
 
     def set_max_slots(self, n: int):
-        """Cap the shared-memory vector slots (>= 2): fewer slots force the schedule to spill (tests)."""
+        """Cap the on-chip vector storage (>= 2): fewer slots force both tree-walking kernels to spill (tests)."""
         self._check(self._lib.cafe_b200_set_option(self._h, OPT_MAX_SLOTS, int(n)), "set_option")
 
     def set_stream(self, cuda_stream_ptr: int):
@@ -220,11 +260,21 @@ class Engine:
         self._check(rc, "cafe_b200_eval")
         return {"score": score.value, "family_lnl": fam, "cat_lk": cat, "n_failed": nf.value, "failed_idx": fidx[fidx >= 0]}
 
+    def fetch_category_likelihoods(self, k: int) -> np.ndarray:
+        """[n_families][k] category likelihoods of the last gamma evaluation (for callers that skipped them in infer)."""
+        out = np.empty((self.n_families, k))
+        self._check(self._lib.cafe_b200_fetch_category_likelihoods(self._h, k, _d(out)), "cafe_b200_fetch_category_likelihoods")
+        return out
+
     def infer_device(self, lambdas, prior, cat_probs, mode, result_ptr: int):
         """Asynchronous evaluation; [sum lnL, n_failed] are written to device memory at result_ptr."""
         lam, k, nl = self._lams(lambdas)
         cp = np.ascontiguousarray(cat_probs if cat_probs is not None else np.ones(k), np.float64)
         pr = np.ascontiguousarray(prior, np.float64)
+        if pr.shape[0] < self.mrf:
+            raise ValueError("prior must have max_root_family_size entries")
+        if cp.shape[0] != k:
+            raise ValueError("one category probability per lambda row")
         self._check(self._lib.cafe_b200_eval_device(self._h, _d(lam), nl, _d(cp), k, _d(pr), mode, C.c_void_p(result_ptr)), "cafe_b200_eval_device")
 
     def reconstruct(self, lambdas, prior_by_size):

@@ -84,9 +84,21 @@ class ShardedLikelihood:
 
 
 def engine_local_eval(eng) -> Callable:
-    """The product path: ``cafe_b200_eval_device`` on the engine's stream, result left in device memory."""
+    """The product path: ``cafe_b200_eval_device``, result left in device memory.
+
+    The engine's kernels must be ordered against the NCCL all-reduce that follows, and NCCL orders against torch's
+    CURRENT stream only.  So the engine is bound to that stream before every evaluation (a no-op when it already is):
+    the library's kernels, the collective and the caller's timing events then share one stream and no event plumbing
+    is needed."""
+    bound = {"stream": None}
+
     def run(lambdas, prior, cat_probs, mode, result):
+        import torch
         if not result.is_cuda:
             raise RuntimeError("the CUDA engine writes its result to device memory")
+        stream = torch.cuda.current_stream(result.device).cuda_stream
+        if bound["stream"] != stream:
+            eng.set_stream(stream)
+            bound["stream"] = stream
         eng.infer_device(lambdas, prior, cat_probs, mode, result.data_ptr())
     return run

@@ -22,13 +22,14 @@
 #ifndef CAFE_B200_H
 #define CAFE_B200_H
 
+#include <stddef.h>
 #include <stdint.h>
 
 #ifdef __cplusplus
 extern "C" {
 #endif
 
-#define CAFE_B200_ABI_VERSION 1
+#define CAFE_B200_ABI_VERSION 2
 
 enum {
     CAFE_B200_OK = 0,
@@ -53,8 +54,9 @@ enum {
                                    reference.  1: exact power-of-two per-family rescaling of every internal-node vector;
                                    identical results wherever the reference does not underflow, and the reference's
                                    "all zero" failure verdict is reproduced from the tracked exponent. */
-    CAFE_B200_OPT_MAX_SLOTS = 2 /* cap the shared-memory vector slots per thread block (>= 2; default: as many as fit).
-                                   Fewer slots force the schedule to spill vectors to device scratch; used by tests. */
+    CAFE_B200_OPT_MAX_SLOTS = 2 /* cap the on-chip vector storage per thread block (>= 2; default: as much as fits): the
+                                   reconstruction kernel keeps `value` shared-memory slots, the pruning kernel parks at most
+                                   `value - 2` partial products in tensor memory.  Less forces spills to device scratch; used by tests. */
 };
 
 /* Species tree, flattened.  Node numbering = the order clade::apply_reverse_level_order visits
@@ -78,7 +80,7 @@ typedef struct cafe_b200_limits {
     int max_matrix_size;       /* max(max_family_size, max_root_family_size)+1 supported      */
     int max_categories;
     int max_nodes;
-    int families_per_tile;     /* families pruned together as matrix columns by one thread block */
+    int families_per_tile;     /* most families pruned together as matrix columns by one thread block */
 } cafe_b200_limits;
 
 int  cafe_b200_abi_version(void);
@@ -92,6 +94,25 @@ int  cafe_b200_device_count(void);
  * device: CUDA ordinal.  The context owns one stream; all work of a call is enqueued on it. */
 int  cafe_b200_create(cafe_b200_ctx** out, const cafe_b200_tree* tree, const int32_t* leaf_counts,
                       int64_t n_families, int n_leaves, int max_family_size, int max_root_family_size, int device);
+
+/* The same over SEVERAL devices of one box, driven by the one host thread the reference's optimizer runs on
+ * ("const int* devices, int n_devices"; section 8e).  Families are split into n_devices contiguous
+ * ranges, device i owning [F*i/n, F*(i+1)/n); every other entry point then works on all shards at once: the host inputs
+ * are staged once, each device builds its matrices and prunes its range concurrently, per-family outputs land in the
+ * caller's arrays at the families' global positions, and the score is the sum of the devices' [sum lnL, #failed]
+ * pairs, added on the host in device-list order (deterministic; 16 bytes per device, no collective library needed).
+ *   leaf_counts  HOST [n_families][n_leaves], elements of count_bytes = 1 (uint8), 2 (uint16) or 4 (int32) bytes.
+ *                On the device counts are 1 byte each when max_family_size <= 255 (else 2): handing over uint8
+ *                moves a quarter of the bytes of int32 (pinned host memory makes the copy asynchronous). */
+int  cafe_b200_create_multi(cafe_b200_ctx** out, const cafe_b200_tree* tree, const void* leaf_counts, int count_bytes,
+                            int64_t n_families, int n_leaves, int max_family_size, int max_root_family_size,
+                            const int* devices, int n_devices);
+int  cafe_b200_n_devices(const cafe_b200_ctx* ctx);
+
+/* Page-locked host memory for inputs / outputs of the calls below (plain malloc'ed memory works too, but is copied
+ * through a driver staging buffer).  NULL when no device / out of memory. */
+void* cafe_b200_alloc_pinned(size_t bytes);
+void  cafe_b200_free_pinned(void* p);
 void cafe_b200_destroy(cafe_b200_ctx* ctx);
 const char* cafe_b200_last_error(const cafe_b200_ctx* ctx);   /* ctx may be NULL: last create() error */
 
@@ -99,16 +120,18 @@ const char* cafe_b200_last_error(const cafe_b200_ctx* ctx);   /* ctx may be NULL
  * The range check (0 <= count <= max_family_size) runs on the device after the copy: on CAFE_B200_ERR_COUNT_RANGE
  * the context holds the rejected matrix and refuses every evaluation until a valid one is set. */
 int  cafe_b200_set_families(cafe_b200_ctx* ctx, const int32_t* leaf_counts, int64_t n_families);
+int  cafe_b200_set_families_ex(cafe_b200_ctx* ctx, const void* leaf_counts, int count_bytes, int64_t n_families);
 
 /* Leaf error model: dense HOST [rows][n_deviations] table indexed by OBSERVED count, i.e. row s =
  * error_model::get_probs(s) (src/error_model.cpp:52-57); deviations are centred, -(nd-1)/2..+(nd-1)/2
- * (src/probability.cpp:185).  probs == NULL removes the error model. */
+ * (src/probability.cpp:185).  probs == NULL removes the error model.  Cheap to call before every evaluation (the
+ * epsilon optimiser edits the model in place): the table is uploaded only when it differs from the last one. */
 int  cafe_b200_set_error_model(cafe_b200_ctx* ctx, const double* probs, int rows, int n_deviations);
 
 int  cafe_b200_set_option(cafe_b200_ctx* ctx, int option, int value);
 
 /* Enqueue on an existing CUDA stream (cudaStream_t passed as void*; NULL = the legacy default stream)
- * instead of the context's own non-blocking stream. */
+ * instead of the context's own non-blocking stream.  Single-device contexts only. */
 int  cafe_b200_set_stream(cafe_b200_ctx* ctx, void* cuda_stream);
 
 /* One evaluation of the likelihood = the body of base_model::infer_family_likelihoods
@@ -128,9 +151,14 @@ int  cafe_b200_eval(cafe_b200_ctx* ctx, const double* lambdas, int n_lambdas, co
                     const double* prior, int mode, double* neg_lnl, double* family_lnl, double* cat_lk,
                     int64_t* n_failed, int64_t* failed_idx, int64_t failed_cap);
 
+/* The category likelihoods [n_families][k] of the LAST cafe_b200_eval in gamma mode, for callers that passed
+ * cat_lk = NULL there (an optimizer needs only the score; _category_likelihoods is read once, after the fit). */
+int  cafe_b200_fetch_category_likelihoods(cafe_b200_ctx* ctx, int n_categories, double* cat_lk);
+
 /* Same evaluation, asynchronous, result left on the device: result_device[0] = sum_i lnL_i over
  * non-failed families, result_device[1] = number of failed families (as a double).  This is the pair a
- * multi-process caller sum-allreduces (NCCL) across its family shards; no host synchronisation. */
+ * multi-process caller sum-allreduces (NCCL) across its family shards; no host synchronisation.  Single-device
+ * contexts only (a multi-device context reduces inside cafe_b200_eval). */
 int  cafe_b200_eval_device(cafe_b200_ctx* ctx, const double* lambdas, int n_lambdas, const double* cat_probs, int n_categories,
                            const double* prior, int mode, double* result_device);
 
@@ -185,15 +213,25 @@ int  cafe_b200_matrix_size(const cafe_b200_ctx* ctx);
  * HOST out [n_families][n_categories][max_root_family_size], index j <-> root size j+1. */
 int  cafe_b200_prune_roots(cafe_b200_ctx* ctx, const double* lambdas, int n_lambdas, int n_categories, double* out);
 
-/* Host-only (no GPU needed): the op list the pruning / reconstruction kernels walk for this tree with
- * n_slots shared-memory slots.  ops_out: [cap][4] = {type, a, b, node}; types: 0 LEAF_SET(a,node) 1 LEAF_MUL
- * 2 GEMM_SET(a,node) 3 GEMM_MUL(a,b,node) 4 SPILL(a->scratch b) 5 FILL(a<-scratch b) 6 RESCALE(a) 7 ROOT(a). */
+/* Host-only (no GPU needed): the op list the reconstruction kernel walks for this tree with n_slots shared-memory
+ * slots.  ops_out: [cap][4] = {type, a, b, node}; types: 0 LEAF_SET(a,node) 1 LEAF_MUL
+ * 2 GEMM_SET(a,node) 3 GEMM_MUL(a,b,node) 4 SPILL(a->scratch b) 5 FILL(a<-scratch b) 6 (end of node) 7 ROOT(a). */
 int  cafe_b200_plan_schedule(const cafe_b200_tree* tree, int n_slots, int* ops_out, int cap, int* n_ops, int* n_spill);
+
+/* Host-only: the stack-machine program the pruning kernel walks.  ops_out: [cap][7] = {type, node, flags, stack,
+ * leaf_begin, n_pre, n_post}; types: 0 LEAVES (vector = product of the n_pre leaf columns listed from leaf_begin),
+ * 1 GEMM (acc = M(node) * vector; acc = [product of n_pre leaves *] [parked(stack) *, flags & 1] acc [* n_post leaves];
+ * flags & 2: park acc at `stack`, else acc is the parent's vector), 2 ROOT.  leaves_out: leaf node ids. */
+int  cafe_b200_plan_program(const cafe_b200_tree* tree, int* ops_out, int cap, int* n_ops, int* leaves_out, int leaves_cap,
+                            int* n_leaf_refs, int* depth);
+
+/* Human-readable description of the launch geometry chosen for this context (groups, ring, tensor-memory use). */
+int  cafe_b200_describe(const cafe_b200_ctx* ctx, char* out, int cap);
 
 /* Counters since create: kernel launches issued by this library, and evaluations. */
 int64_t cafe_b200_launch_count(const cafe_b200_ctx* ctx);
 
-/* Device time (ms, CUDA events on the context's stream) of the phases of the LAST cafe_b200_eval /
+/* Device time (ms, CUDA events on the context's streams, max over devices) of the phases of the LAST cafe_b200_eval /
  * cafe_b200_prune_roots / cafe_b200_reconstruct call: [0] matrix build, [1] pruning, [2] reduce,
  * [3] reconstruction.  Valid after the call returned (it synchronises). */
 int  cafe_b200_last_timings(const cafe_b200_ctx* ctx, double* ms4);

@@ -38,6 +38,8 @@ void initialize_prior(root_equilibrium_distribution* prior, const std::map<int, 
     prior->initialize(&rd);
 }
 
+bool g_device_branch_probabilities = false;
+
 struct count_row_hash {
     size_t operator()(const std::vector<int>& v) const
     {
@@ -48,6 +50,8 @@ struct count_row_hash {
 };
 
 }  // namespace
+
+void cuda_models_use_device_branch_probabilities(bool on) { g_device_branch_probabilities = on; }
 
 // ------------------------------------------------------------------------------------------------------
 // cuda_bridge
@@ -84,7 +88,19 @@ cuda_bridge::cuda_bridge(const clade* p_tree, int max_family_size, int max_root_
 
 cuda_bridge::~cuda_bridge()
 {
+    release();
+}
+
+void cuda_bridge::release()
+{
     if (_ctx) cafe_b200_destroy(_ctx);
+    _ctx = nullptr;
+    cafe_b200_free_pinned(_h_family_lnl);
+    cafe_b200_free_pinned(_h_cat_lk);
+    _h_family_lnl = _h_cat_lk = nullptr;
+    _cat_lk_capacity = 0;
+    _bound = nullptr;
+    _bound_size = 0;
 }
 
 void cuda_bridge::check(int rc, const char* what) const
@@ -93,9 +109,48 @@ void cuda_bridge::check(int rc, const char* what) const
         throw std::runtime_error(std::string(what) + " failed (" + std::to_string(rc) + "): " + cafe_b200_last_error(_ctx));
 }
 
+std::vector<int> cuda_bridge::devices_from_environment()
+{
+    std::vector<int> devices;
+    if (const char* e = getenv("CAFE_B200_DEVICES")) {
+        std::string list = e;
+        if (list == "all") {
+            for (int d = 0; d < cafe_b200_device_count(); ++d) devices.push_back(d);
+        }
+        else {
+            size_t pos = 0;
+            while (pos < list.size()) {
+                size_t comma = list.find(',', pos);
+                if (comma == std::string::npos) comma = list.size();
+                if (comma > pos) devices.push_back(atoi(list.substr(pos, comma - pos).c_str()));
+                pos = comma + 1;
+            }
+        }
+    }
+    if (devices.empty()) {
+        int device = 0;
+        if (const char* e = getenv("CAFE_B200_DEVICE")) device = atoi(e);
+        devices.push_back(device);
+    }
+    return devices;
+}
+
+int cuda_bridge::device_count() const { return _ctx ? cafe_b200_n_devices(_ctx) : 0; }
+
+// Counts of a spread of at most 64 rows: cheap next to an evaluation (a full pass costs F x leaves map look-ups),
+// enough to notice a bound vector that was edited in place.
+size_t cuda_bridge::fingerprint(const std::vector<gene_family>& families) const
+{
+    size_t h = 1469598103934665603ull;
+    const size_t n = families.size(), step = std::max<size_t>(1, n / 64);
+    for (size_t i = 0; i < n; i += step)
+        for (const clade* leaf : _leaves) h = (h ^ (size_t)families[i].get_species_size(leaf->get_taxon_name())) * 1099511628211ull;
+    return h;
+}
+
 void cuda_bridge::bind(const std::vector<gene_family>& families)
 {
-    if (_ctx && _bound == &families && _bound_size == families.size()) return;
+    if (_ctx && _bound == &families && _bound_size == families.size() && _bound_fingerprint == fingerprint(families)) return;
     const size_t nl = _leaves.size();
     std::vector<int> rows(families.size() * nl);
     for (size_t i = 0; i < families.size(); ++i)
@@ -103,13 +158,12 @@ void cuda_bridge::bind(const std::vector<gene_family>& families)
     bind_rows(rows, families.size());
     _bound = &families;
     _bound_size = families.size();
+    _bound_fingerprint = fingerprint(families);
 }
 
 void cuda_bridge::bind_rows(const std::vector<int>& rows, size_t n_rows)
 {
-    if (_ctx) { cafe_b200_destroy(_ctx); _ctx = nullptr; }
-    _bound = nullptr;
-    _bound_size = 0;
+    release();
 
     // Identical count rows are evaluated once.  The reference does this for the base model only
     // (build_reference_list, src/base_model.cpp:27-51, O(F^2)); identical inputs give identical outputs for
@@ -119,6 +173,7 @@ void cuda_bridge::bind_rows(const std::vector<int>& rows, size_t n_rows)
     std::vector<int32_t> counts;
     _unique_of.resize(n_rows);
     _max_count = 0;
+    int min_count = 0;
     std::vector<int> row(nl);
     for (size_t i = 0; i < n_rows; ++i) {
         row.assign(rows.begin() + i * nl, rows.begin() + (i + 1) * nl);
@@ -126,7 +181,7 @@ void cuda_bridge::bind_rows(const std::vector<int>& rows, size_t n_rows)
         if (it == seen.end()) {
             it = seen.emplace(row, seen.size()).first;
             counts.insert(counts.end(), row.begin(), row.end());
-            for (int x : row) _max_count = std::max(_max_count, x);
+            for (int x : row) { _max_count = std::max(_max_count, x); min_count = std::min(min_count, x); }
         }
         _unique_of[i] = it->second;
     }
@@ -140,13 +195,24 @@ void cuda_bridge::bind_rows(const std::vector<int>& rows, size_t n_rows)
     t.leaf_col = _leaf_col.data();
     t.branch = _branch.data();
     t.lambda_index = _lambda_index.data();
-    int device = 0;
-    if (const char* e = getenv("CAFE_B200_DEVICE")) device = atoi(e);
-    int rc = cafe_b200_create(&_ctx, &t, counts.data(), (int64_t)_n_unique, (int)nl, _mf, _mrf, device);
+    const std::vector<int> devices = devices_from_environment();
+    // counts travel as one byte each when they fit (the device stores them that way for max_family_size <= 255)
+    std::vector<uint8_t> narrow;
+    const void* data = counts.data();
+    int width = 4;
+    if (min_count >= 0 && _max_count <= 255) {
+        narrow.assign(counts.begin(), counts.end());
+        data = narrow.data();
+        width = 1;
+    }
+    int rc = cafe_b200_create_multi(&_ctx, &t, data, width, (int64_t)_n_unique, (int)nl, _mf, _mrf, devices.data(), (int)devices.size());
     if (rc != CAFE_B200_OK) {
         _ctx = nullptr;
         throw std::runtime_error(std::string("cafe_b200_create failed (") + std::to_string(rc) + "): " + cafe_b200_last_error(nullptr));
     }
+    _h_family_lnl = static_cast<double*>(cafe_b200_alloc_pinned(std::max<size_t>(1, _n_unique) * sizeof(double)));
+    if (!_h_family_lnl) throw std::runtime_error("cafe_b200_alloc_pinned failed");
+    _failed_idx.assign(std::max<size_t>(1, _n_unique), 0);
 }
 
 void cuda_bridge::set_error_model(const error_model* p_error_model)
@@ -186,20 +252,45 @@ std::vector<double> cuda_bridge::prior_table(const root_equilibrium_distribution
 }
 
 long cuda_bridge::evaluate(const std::vector<double>& lambdas, const std::vector<double>& cat_probs, const std::vector<double>& prior, int mode,
-                           std::vector<double>& family_lnl, std::vector<double>& cat_lk, std::vector<char>& failed)
+                           std::vector<char>& failed)
 {
     const int k = (int)cat_probs.size();
-    family_lnl.assign(_n_unique, 0.0);
-    cat_lk.assign(mode == CAFE_B200_GAMMA_LINSUM ? _n_unique * k : 0, 0.0);
-    failed.assign(_n_unique, 0);
     double neg_lnl = 0.0;
     int64_t n_failed = 0;
-    std::vector<int64_t> failed_idx(_n_unique ? _n_unique : 1);
-    check(cafe_b200_eval(_ctx, lambdas.data(), (int)_order.size(), cat_probs.data(), k, prior.data(), mode, &neg_lnl, family_lnl.data(),
-                         cat_lk.empty() ? nullptr : cat_lk.data(), &n_failed, failed_idx.data(), (int64_t)failed_idx.size()),
+    static_assert(sizeof(long long) == sizeof(int64_t), "64-bit indices");
+    // only the per-family lnL comes back with every evaluation (the caller sums it in family order); the category
+    // likelihoods stay on the device until somebody asks (category_likelihoods())
+    check(cafe_b200_eval(_ctx, lambdas.data(), (int)_order.size(), cat_probs.data(), k, prior.data(), mode, &neg_lnl, _h_family_lnl, nullptr,
+                         &n_failed, reinterpret_cast<int64_t*>(_failed_idx.data()), (int64_t)_failed_idx.size()),
           "cafe_b200_eval");
-    for (int64_t i = 0; i < n_failed; ++i) failed[failed_idx[i]] = 1;
+    _last_k = mode == CAFE_B200_GAMMA_LINSUM ? k : 0;
+    _cat_lk_fetched = false;
+    ++_evaluations;
+    double ms[4] = {0, 0, 0, 0};
+    if (cafe_b200_last_timings(_ctx, ms) == CAFE_B200_OK) _device_seconds += (ms[0] + ms[1] + ms[2]) * 1e-3;
+    failed.clear();
+    if (n_failed > 0) {
+        failed.assign(_n_unique, 0);
+        for (int64_t i = 0; i < n_failed; ++i) failed[_failed_idx[i]] = 1;
+    }
     return (long)n_failed;
+}
+
+const double* cuda_bridge::category_likelihoods()
+{
+    if (_last_k <= 0) throw std::runtime_error("category_likelihoods: the last evaluation was not a gamma evaluation");
+    if (!_cat_lk_fetched) {
+        const size_t need = std::max<size_t>(1, _n_unique * _last_k);
+        if (need > _cat_lk_capacity) {
+            cafe_b200_free_pinned(_h_cat_lk);
+            _h_cat_lk = static_cast<double*>(cafe_b200_alloc_pinned(need * sizeof(double)));
+            if (!_h_cat_lk) throw std::runtime_error("cafe_b200_alloc_pinned failed");
+            _cat_lk_capacity = need;
+        }
+        check(cafe_b200_fetch_category_likelihoods(_ctx, _last_k, _h_cat_lk), "cafe_b200_fetch_category_likelihoods");
+        _cat_lk_fetched = true;
+    }
+    return _h_cat_lk;
 }
 
 std::vector<double> cuda_bridge::root_max(const std::vector<double>& lambdas)
@@ -252,31 +343,47 @@ double cuda_base_model::infer_family_likelihoods(root_equilibrium_distribution* 
 
     _bridge.bind(*_p_gene_families);
     _bridge.set_error_model(_p_error_model);                                       // the epsilon optimiser edits it in place between calls
-    std::vector<double> family_lnl, cat_lk;
     std::vector<char> failed;
     _bridge.evaluate(_bridge.lambda_table(_p_lambda, {1.0}), {1.0}, cuda_bridge::prior_table(prior, _max_root_family_size),
-                     CAFE_B200_BASE_LOGMAX, family_lnl, cat_lk, failed);
+                     CAFE_B200_BASE_LOGMAX, failed);
 
-    const size_t F = _p_gene_families->size();
-    results.resize(F);
-    std::vector<double> all_families_likelihood(F);
-    for (size_t i = 0; i < F; ++i) {
-        all_families_likelihood[i] = family_lnl[_bridge.unique_of(i)];
-        results[i] = family_info_stash(_p_gene_families->at(i).id(), 0.0, 0.0, 0.0, all_families_likelihood[i], false);
-    }
     // summed on the host in family order, as the reference does (src/base_model.cpp:107)
-    double final_likelihood = -std::accumulate(all_families_likelihood.begin(), all_families_likelihood.end(), 0.0);
+    const size_t F = _p_gene_families->size();
+    const double* family_lnl = _bridge.family_lnl();
+    double sum = 0.0;
+    for (size_t i = 0; i < F; ++i) sum += family_lnl[_bridge.unique_of(i)];
+    const double final_likelihood = -sum;
+    _results_stale = true;
     _monitor.Event_InferenceAttempt_Complete(final_likelihood);
     return final_likelihood;
+}
+
+void cuda_base_model::materialize_results()
+{
+    if (!_results_stale) return;
+    const size_t F = _p_gene_families->size();
+    const double* family_lnl = _bridge.family_lnl();
+    results.resize(F);
+    for (size_t i = 0; i < F; ++i)
+        results[i] = family_info_stash(_p_gene_families->at(i).id(), 0.0, 0.0, 0.0, family_lnl[_bridge.unique_of(i)], false);      // src/base_model.cpp:105
+    _results_stale = false;
+}
+
+void cuda_base_model::write_family_likelihoods(std::ostream& ost)
+{
+    materialize_results();
+    base_model::write_family_likelihoods(ost);
 }
 
 reconstruction* cuda_base_model::reconstruct_ancestral_states(const std::vector<gene_family>& families, matrix_cache* p_calc, root_equilibrium_distribution* p_prior)
 {
     _monitor.Event_Reconstruction_Started("Base");
     auto result = new base_model_reconstruction();
-    // callers read transition matrices from *p_calc afterwards (compute_viterbi_sum, src/execute.cpp:158-170)
-    p_calc->precalculate_matrices(get_lambda_values(_p_lambda), _p_tree->get_branch_lengths());
+    // callers read transition matrices from *p_calc afterwards (compute_viterbi_sum, src/execute.cpp:158-170) unless
+    // they take the branch probabilities from the device
+    if (!g_device_branch_probabilities) p_calc->precalculate_matrices(get_lambda_values(_p_lambda), _p_tree->get_branch_lengths());
 
+    materialize_results();                                                         // before the bridge is re-bound to `families`
     _bridge.bind(families);
     const int lim = std::min(_max_family_size, _max_root_family_size) + 1;         // src/gene_family_reconstructor.cpp:41-56
     std::vector<int> states;
@@ -324,46 +431,80 @@ double cuda_gamma_model::infer_family_likelihoods(root_equilibrium_distribution*
 {
     _monitor.Event_InferenceAttempt_Started();
     results.clear();
+    _results_stale = _cat_lk_stale = false;
     if (!can_infer()) {                                                             // src/gamma_core.cpp:175-179
         _monitor.Event_InferenceAttempt_InvalidValues();
         return -log(0);
     }
     initialize_prior(prior, root_distribution_map, _max_root_family_size);
 
-    const std::vector<double> multipliers = get_lambda_multipliers();
-    const std::vector<double> probs = cat_probs();
-    const size_t k = probs.size();
+    _last_multipliers = get_lambda_multipliers();
+    _last_probs = cat_probs();
     _bridge.bind(*_p_gene_families);
     _bridge.set_error_model(_p_error_model);
-    std::vector<double> family_lnl, cat_lk;
     std::vector<char> failed;
-    const long n_failed = _bridge.evaluate(_bridge.lambda_table(p_lambda, multipliers), probs, cuda_bridge::prior_table(prior, _max_root_family_size),
-                                           CAFE_B200_GAMMA_LINSUM, family_lnl, cat_lk, failed);
+    const long n_failed = _bridge.evaluate(_bridge.lambda_table(p_lambda, _last_multipliers), _last_probs,
+                                           cuda_bridge::prior_table(prior, _max_root_family_size), CAFE_B200_GAMMA_LINSUM, failed);
 
     const size_t F = _p_gene_families->size();
-    _cat_lk.assign(F, std::vector<double>());
+    _cat_lk.clear();
+    _last_failed = n_failed > 0;
     if (n_failed > 0) {                                                             // src/gamma_core.cpp:227-236
         for (size_t i = 0; i < F; ++i)
             if (failed[_bridge.unique_of(i)]) _monitor.Event_InferenceAttempt_Saturation(_p_gene_families->at(i).id());
         return -log(0);
     }
-    std::vector<double> all_bundles_likelihood(F);
-    for (size_t i = 0; i < F; ++i) {
-        const double* cl = &cat_lk[_bridge.unique_of(i) * k];
-        _cat_lk[i].assign(cl, cl + k);
-        const double family_likelihood = std::accumulate(cl, cl + k, 0.0);         // src/gamma_core.cpp:207
-        // posterior: the reference multiplies by the category probability a second time (src/gamma_core.cpp:97-109)
-        double denominator = 0.0;
-        for (size_t c = 0; c < k; ++c) denominator += cl[c] * probs[c];
-        for (size_t c = 0; c < k; ++c) {
-            const double posterior = cl[c] * probs[c] / denominator;
-            results.push_back(family_info_stash(_p_gene_families->at(i).id(), multipliers[c], cl[c], family_likelihood, posterior, posterior > 0.95));
-        }
-        all_bundles_likelihood[i] = std::log(family_likelihood);
-    }
-    double final_likelihood = -std::accumulate(all_bundles_likelihood.begin(), all_bundles_likelihood.end(), 0.0);
+    // lnL_i = log(sum_k cat_lk[i][k]) comes from the device per unique family (src/gamma_core.cpp:207,218); the sum
+    // over families is formed on the host in family order, as the reference forms it (src/gamma_core.cpp:244)
+    const double* family_lnl = _bridge.family_lnl();
+    double sum = 0.0;
+    for (size_t i = 0; i < F; ++i) sum += family_lnl[_bridge.unique_of(i)];
+    const double final_likelihood = -sum;
+    _results_stale = _cat_lk_stale = true;
     _monitor.Event_InferenceAttempt_Complete(final_likelihood);
     return final_likelihood;
+}
+
+const std::vector<std::vector<double>>& cuda_gamma_model::category_likelihoods()
+{
+    if (_cat_lk_stale) {
+        const size_t F = _p_gene_families->size(), k = _last_probs.size();
+        const double* cat_lk = _bridge.category_likelihoods();
+        _cat_lk.assign(F, std::vector<double>());
+        for (size_t i = 0; i < F; ++i) {
+            const double* cl = cat_lk + _bridge.unique_of(i) * k;
+            _cat_lk[i].assign(cl, cl + k);
+        }
+        _cat_lk_stale = false;
+    }
+    return _cat_lk;
+}
+
+void cuda_gamma_model::materialize_results()
+{
+    if (!_results_stale) return;
+    const std::vector<std::vector<double>>& all = category_likelihoods();
+    const size_t F = _p_gene_families->size(), k = _last_probs.size();
+    results.clear();
+    results.reserve(F * k);
+    for (size_t i = 0; i < F; ++i) {
+        const std::vector<double>& cl = all[i];
+        const double family_likelihood = std::accumulate(cl.begin(), cl.end(), 0.0);     // src/gamma_core.cpp:207
+        // posterior: the reference multiplies by the category probability a second time (src/gamma_core.cpp:97-109)
+        double denominator = 0.0;
+        for (size_t c = 0; c < k; ++c) denominator += cl[c] * _last_probs[c];
+        for (size_t c = 0; c < k; ++c) {
+            const double posterior = cl[c] * _last_probs[c] / denominator;
+            results.push_back(family_info_stash(_p_gene_families->at(i).id(), _last_multipliers[c], cl[c], family_likelihood, posterior, posterior > 0.95));
+        }
+    }
+    _results_stale = false;
+}
+
+void cuda_gamma_model::write_family_likelihoods(std::ostream& ost)
+{
+    materialize_results();
+    gamma_model::write_family_likelihoods(ost);
 }
 
 reconstruction* cuda_gamma_model::reconstruct_ancestral_states(const std::vector<gene_family>& families, matrix_cache* p_calc, root_equilibrium_distribution* p_prior)
@@ -373,11 +514,15 @@ reconstruction* cuda_gamma_model::reconstruct_ancestral_states(const std::vector
     const std::vector<double> probs = cat_probs();
     const size_t k = multipliers.size();
 
-    std::vector<double> all;                                                        // src/gamma_core.cpp:305-315
-    for (double multiplier : multipliers)
-        for (double lam : get_lambda_values(_p_lambda)) all.push_back(lam * multiplier);
-    p_calc->precalculate_matrices(all, _p_tree->get_branch_lengths());
+    if (!g_device_branch_probabilities) {
+        std::vector<double> all;                                                    // src/gamma_core.cpp:305-315
+        for (double multiplier : multipliers)
+            for (double lam : get_lambda_values(_p_lambda)) all.push_back(lam * multiplier);
+        p_calc->precalculate_matrices(all, _p_tree->get_branch_lengths());
+    }
 
+    // the last evaluation's outputs leave the device before the bridge is re-bound to `families`
+    if (!_last_failed && (_results_stale || _cat_lk_stale)) { category_likelihoods(); materialize_results(); }
     _bridge.bind(families);
     const int lim = std::min(_max_family_size, _max_root_family_size) + 1;
     std::vector<int> states;
@@ -486,8 +631,7 @@ std::vector<double> compute_pvalues_cuda(const clade* p_tree, const std::vector<
 
     // (3) sort each conditional distribution, upper_bound, max over root sizes (src/probability.cpp:310, 379-409)
     std::vector<double> result(families.size());
-    int device = 0;
-    if (const char* e = getenv("CAFE_B200_DEVICE")) device = atoi(e);
+    const int device = cuda_bridge::devices_from_environment()[0];
     int rc = cafe_b200_pvalues(device, cond.data(), mxr, nsim, observed.data(), (int64_t)observed.size(), result.data());
     if (rc != CAFE_B200_OK) throw std::runtime_error(std::string("cafe_b200_pvalues failed (") + std::to_string(rc) + "): " + cafe_b200_last_error(nullptr));
     return result;

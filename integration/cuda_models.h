@@ -39,6 +39,10 @@ class root_equilibrium_distribution;
 
 //! Flattened (tree, de-duplicated families) and the device context that holds them.
 //! One bridge per model object; it is rebuilt when the family vector it was built for changes.
+//!
+//! Devices: the CUDA ordinals listed in the environment variable CAFE_B200_DEVICES ("0,1,2,3", or "all"); default
+//! device 0 (CAFE_B200_DEVICE is still honoured for a single ordinal).  With several devices the unique families are
+//! split into contiguous ranges, one per device (cafe_b200_create_multi); nothing else changes for the caller.
 class cuda_bridge {
 public:
     cuda_bridge(const clade* p_tree, int max_family_size, int max_root_family_size);
@@ -46,13 +50,16 @@ public:
     cuda_bridge(const cuda_bridge&) = delete;
     cuda_bridge& operator=(const cuda_bridge&) = delete;
 
-    //! (Re)creates the device context if `families` is not the vector the current one was built from.
+    //! (Re)creates the device context if `families` is not the vector the current one was built from (same address,
+    //! same size, same counts in a sample of its rows).  Call invalidate() after editing a bound vector in place.
     void bind(const std::vector<gene_family>& families);
+    void invalidate() { _bound = nullptr; }
 
     //! Same for raw count rows [n_rows][leaves in leaf_nodes() order] (simulated families never become gene_family objects).
     void bind_rows(const std::vector<int>& rows, size_t n_rows);
 
-    //! Uploads the error model as a dense [observed count][deviation] table (or removes it).
+    //! Hands the error model over as a dense [observed count][deviation] table (or removes it); the library uploads
+    //! it only when it differs from the previous one, so this is called before every evaluation.
     void set_error_model(const error_model* p_error_model);
 
     //! lambdas[k][node] = (p_lambda * multiplier_k)->get_value_for_clade(node)   (src/lambda.h:45-48,76-84)
@@ -61,10 +68,14 @@ public:
     //! prior[j] = (double)prior->compute(j), j = 0..n-1   (a float widened, src/root_equilibrium_distribution.h:15)
     static std::vector<double> prior_table(const root_equilibrium_distribution* prior, int n);
 
-    //! One evaluation on the device.  Outputs are per UNIQUE family; expand with unique_of().
-    //! Returns the number of unique families whose pruning failed (gamma mode).
+    //! One evaluation on the device.  family_lnl() then holds lnL per UNIQUE family (expand with unique_of()); the
+    //! category likelihoods stay on the device until category_likelihoods() asks for them.
+    //! Returns the number of unique families whose pruning failed (gamma mode); failed[] flags them.
     long evaluate(const std::vector<double>& lambdas, const std::vector<double>& cat_probs, const std::vector<double>& prior, int mode,
-                  std::vector<double>& family_lnl, std::vector<double>& cat_lk, std::vector<char>& failed);
+                  std::vector<char>& failed);
+    const double* family_lnl() const { return _h_family_lnl; }
+    //! [unique family][category] of the LAST gamma evaluation (fetched from the device on first use).
+    const double* category_likelihoods();
 
     //! max_j of the root vector of every UNIQUE family under one lambda set (no categories, no prior): the
     //! likelihood compute_pvalues uses (src/probability.cpp:308, 399).
@@ -84,6 +95,13 @@ public:
     const std::vector<const clade*>& nodes() const { return _order; }             // apply_reverse_level_order, root last
     int max_family_size() const { return _mf; }
     int max_root_family_size() const { return _mrf; }
+    int device_count() const;
+    //! device time (CUDA events: matrix build + pruning + reduction) and number of evaluate() calls so far
+    double device_seconds() const { return _device_seconds; }
+    long evaluations() const { return _evaluations; }
+
+    //! CUDA ordinals from CAFE_B200_DEVICES / CAFE_B200_DEVICE (see above).
+    static std::vector<int> devices_from_environment();
 
 private:
     const clade* _p_tree;
@@ -95,13 +113,31 @@ private:
     std::vector<double> _branch;
     const std::vector<gene_family>* _bound = nullptr;
     size_t _bound_size = 0;
+    size_t _bound_fingerprint = 0;
     std::vector<size_t> _unique_of;
     size_t _n_unique = 0;
     int _max_count = 0;
     cafe_b200_ctx* _ctx = nullptr;
+    // page-locked result buffers, sized at bind
+    double* _h_family_lnl = nullptr;
+    double* _h_cat_lk = nullptr;
+    size_t _cat_lk_capacity = 0;
+    int _last_k = 0;
+    bool _cat_lk_fetched = false;
+    std::vector<long long> _failed_idx;
+    double _device_seconds = 0.0;
+    long _evaluations = 0;
 
     void check(int rc, const char* what) const;
+    size_t fingerprint(const std::vector<gene_family>& families) const;
+    void release();
 };
+
+//! Tell the drop-in that branch probabilities come from compute_branch_probabilities_cuda (below), i.e. that nobody
+//! reads the host matrix_cache after reconstruct_ancestral_states (src/execute.cpp:158-170): the reconstruction then
+//! skips the host-side precalculate_matrices (seconds of CPU work for k = 4).  Default: false (the cache is filled, as
+//! an unmodified execute.cpp expects).
+void cuda_models_use_device_branch_probabilities(bool on);
 
 class cuda_base_model : public base_model {
 public:
@@ -110,10 +146,17 @@ public:
 
     double infer_family_likelihoods(root_equilibrium_distribution* prior, const std::map<int, int>& root_distribution_map, const lambda* p_lambda) override;
     reconstruction* reconstruct_ancestral_states(const std::vector<gene_family>& families, matrix_cache* p_calc, root_equilibrium_distribution* p_prior) override;
+    void write_family_likelihoods(std::ostream& ost) override;
     std::string name() const override { return "Base"; }
+
+    //! Fills model::results from the last evaluation.  The reference rebuilds this vector in every evaluation
+    //! (src/base_model.cpp:105) although only write_family_likelihoods reads it; here it is built on demand.
+    void materialize_results();
+    cuda_bridge& bridge() { return _bridge; }
 
 private:
     cuda_bridge _bridge;
+    bool _results_stale = false;
 };
 
 class cuda_gamma_model : public gamma_model {
@@ -125,16 +168,22 @@ public:
 
     double infer_family_likelihoods(root_equilibrium_distribution* prior, const std::map<int, int>& root_distribution_map, const lambda* p_lambda) override;
     reconstruction* reconstruct_ancestral_states(const std::vector<gene_family>& families, matrix_cache* p_calc, root_equilibrium_distribution* p_prior) override;
+    void write_family_likelihoods(std::ostream& ost) override;
     std::string name() const override { return "Gamma"; }
 
-    //! category likelihoods of the last evaluation, per family (the reference keeps these private)
-    const std::vector<std::vector<double>>& category_likelihoods() const { return _cat_lk; }
+    //! category likelihoods of the last evaluation, per family (the reference keeps these private); built on demand
+    const std::vector<std::vector<double>>& category_likelihoods();
+    //! Fills model::results (F x k stashes, src/gamma_core.cpp:209-241) from the last evaluation, on demand.
+    void materialize_results();
+    cuda_bridge& bridge() { return _bridge; }
 
 private:
     cuda_bridge _bridge;
     bool _explicit_categories;
     std::vector<double> _explicit_cat_probs;
     std::vector<std::vector<double>> _cat_lk;
+    std::vector<double> _last_multipliers, _last_probs;
+    bool _results_stale = false, _cat_lk_stale = false, _last_failed = false;
 
     std::vector<double> cat_probs() const;
 };

@@ -363,6 +363,12 @@ int cmd_eval(const args_t& a)
         double dt = std::chrono::duration<double>(std::chrono::steady_clock::now() - t0).count();
         best = std::min(best, dt); total += dt;
     }
+#ifdef WITH_CUDA_MODELS
+    // the CUDA models build model::results on demand (write_family_likelihoods); the dumps below read it directly
+    if (auto cb = dynamic_cast<cuda_base_model*>(m)) cb->materialize_results();
+    if (auto cg = dynamic_cast<cuda_gamma_model*>(m)) cg->materialize_results();
+    if (a.integer("cuda", 0) && a.has("viterbi")) cuda_models_use_device_branch_probabilities(true);
+#endif
     dumper d(a.str("dump"));
     size_t F = s.data.gene_families.size();
     auto gm = dynamic_cast<gamma_model*>(m);
@@ -472,7 +478,16 @@ int cmd_fit(const args_t& a)
     printf("{"); print_setup(s);
     printf("\"model\": \"%s\", ", m->name().c_str()); jarr("values", result.values);
     printf(", \"score\": "); jnum(result.score);
-    printf(", \"iterations\": %d, \"evaluations\": %d, \"seconds\": %.3f, \"seconds_in_score\": %.3f}\n", result.num_iterations, cs.evals, dt, cs.seconds);
+    printf(", \"iterations\": %d, \"evaluations\": %d, \"seconds\": %.6f, \"seconds_in_score\": %.6f", result.num_iterations, cs.evals, dt, cs.seconds);
+#ifdef WITH_CUDA_MODELS
+    {
+        cuda_bridge* br = nullptr;
+        if (auto cb = dynamic_cast<cuda_base_model*>(m)) br = &cb->bridge();
+        if (auto cg = dynamic_cast<cuda_gamma_model*>(m)) br = &cg->bridge();
+        if (br) printf(", \"devices\": %d, \"device_evaluations\": %ld, \"device_seconds\": %.6f", br->device_count(), br->evaluations(), br->device_seconds());
+    }
+#endif
+    printf("}\n");
     return 0;
 }
 

@@ -299,20 +299,23 @@ def test_set_families_and_launch_accounting(mammal):
     flat, counts = mammal["tree"], mammal["counts"][:1000]
     prior = orc.prior_uniform(mammal["mrf"])
     with engine.Engine(flat, counts, mammal["mf"], mammal["mrf"]) as eng:
+        assert eng.launches == 1                      # create: the device-side ingest (narrowing + range check) of the counts
         a = eng.infer([[0.002]], prior)
-        n1 = eng.launches
-        assert n1 == 4                                # matrix build, prune, finalize, final sum
+        assert eng.launches == 5                      # + matrix build, prune, finalize, final sum
         eng.set_families(counts[::-1].copy())
         b = eng.infer([[0.002]], prior)
-        assert eng.launches == 9                      # + the device-side range check of the uploaded counts
+        assert eng.launches == 10                     # + ingest of the new counts + the four kernels of an evaluation
+        eng.set_families(counts[::-1].astype(np.uint8))     # counts may travel as one byte each
+        c = eng.infer([[0.002]], prior)
+        assert np.array_equal(c["family_lnl"], b["family_lnl"])
         assert np.array_equal(b["family_lnl"], a["family_lnl"][::-1])
         t = eng.last_timings_ms()
         assert t["prune"] > 0 and t["matrix_build"] > 0
 
 
-def test_three_group_layout_matches_two_group_results(mammal, monkeypatch):
-    """The experimental 48-family tile layout (CAFE_B200_GROUPS=3: three consumer groups, two vector slots, more spills)
-    computes the same numbers as the shipped one: same MMA tiles and the same order of every product."""
+def test_two_and_three_group_layouts_give_identical_results(mammal, monkeypatch):
+    """The 32-family tile layout (two consumer groups, what matrix sizes above 160 use) computes the same numbers as
+    the default 48-family one: same MMA tiles and the same order of every product."""
     flat, counts = mammal["tree"], mammal["counts"][:1500]
     mf, mrf = mammal["mf"], mammal["mrf"]
     freq, rate = orc.get_gamma(3, 0.6)
@@ -321,8 +324,10 @@ def test_three_group_layout_matches_two_group_results(mammal, monkeypatch):
     with engine.Engine(flat, counts, mf, mrf) as eng:
         two = eng.infer(lams, prior, freq, engine.GAMMA_LINSUM)
         roots2 = eng.prune_roots(lams[:1])
-    monkeypatch.setenv("CAFE_B200_GROUPS", "3")
+        assert "groups=3" in eng.describe()
+    monkeypatch.setenv("CAFE_B200_GEOM", "2,2,2")
     with engine.Engine(flat, counts, mf, mrf) as eng:
+        assert "groups=2" in eng.describe()
         three = eng.infer(lams, prior, freq, engine.GAMMA_LINSUM)
         roots3 = eng.prune_roots(lams[:1])
     assert np.array_equal(two["cat_lk"], three["cat_lk"], equal_nan=True)

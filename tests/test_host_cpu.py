@@ -24,9 +24,9 @@ def test_library_exports_every_declared_symbol():
     for name in sorted(declared):
         assert hasattr(lib, name), f"{name} declared in include/cafe_b200.h but not exported"
     assert declared == set(engine.EXPORTS) | {"cafe_b200_plan_schedule"}
-    assert lib.cafe_b200_abi_version() == 1
+    assert lib.cafe_b200_abi_version() == 2
     lim = engine.limits()
-    assert lim["families_per_tile"] == 32 and lim["max_matrix_size"] >= 151
+    assert lim["families_per_tile"] == 48 and lim["max_matrix_size"] >= 512
 
 
 @pytest.mark.skipif(engine.load_library().cafe_b200_device_count() > 0, reason="a GPU is present")
@@ -46,12 +46,8 @@ def test_create_rejects_bad_input():
 def plan(tree, n_slots):
     lib = engine.load_library()
     lib.cafe_b200_plan_schedule.restype = C.c_int
-    arrs = [np.ascontiguousarray(a, np.int32) for a in (tree.parent, tree.child_offset, tree.child_list, tree.leaf_col)]
-    br = np.ascontiguousarray(tree.branch, np.float64)
-    li = np.ascontiguousarray(tree.lambda_index, np.int32)
     ip = C.POINTER(C.c_int)
-    ts = engine._Tree(tree.n_nodes, arrs[0].ctypes.data_as(ip), arrs[1].ctypes.data_as(ip), arrs[2].ctypes.data_as(ip),
-                      arrs[3].ctypes.data_as(ip), br.ctypes.data_as(C.POINTER(C.c_double)), li.ctypes.data_as(ip))
+    ts, _keep = engine.tree_struct(tree)
     cap = 16 * tree.n_nodes + 64
     ops = np.zeros((cap, 4), np.int32)
     n_ops = C.c_int()
@@ -59,6 +55,60 @@ def plan(tree, n_slots):
     rc = lib.cafe_b200_plan_schedule(C.byref(ts), n_slots, ops.ctypes.data_as(ip), cap, C.byref(n_ops), C.byref(n_spill))
     assert rc == 0
     return ops[:n_ops.value], n_spill.value
+
+
+def plan_program(tree):
+    """(ops [n][7], leaf node ids, stack depth) of the pruning kernel's stack-machine program."""
+    lib = engine.load_library()
+    ip = C.POINTER(C.c_int)
+    ts, _keep = engine.tree_struct(tree)
+    cap = 4 * tree.n_nodes + 8
+    ops = np.zeros((cap, 7), np.int32)
+    leaves = np.zeros(cap, np.int32)
+    n_ops, n_leaf, depth = C.c_int(), C.c_int(), C.c_int()
+    rc = lib.cafe_b200_plan_program(C.byref(ts), ops.ctypes.data_as(ip), cap, C.byref(n_ops), leaves.ctypes.data_as(ip), cap, C.byref(n_leaf),
+                                    C.byref(depth))
+    assert rc == 0
+    return ops[:n_ops.value], leaves[:n_leaf.value], depth.value
+
+
+def interpret_program(tree, ops, leaves, depth, counts_row, lambdas, mf, mrf):
+    """Run the stack-machine program on the CPU for one family: what the pruning kernel does, in numpy."""
+    n = max(mf, mrf) + 1
+    mats = {v: orc.build_matrix(n, lambdas[tree.lambda_index[v]], tree.branch[v])[:, :mf + 1] for v in range(tree.n_nodes - 1)}
+    column = lambda leaf: mats[leaf][:, counts_row[tree.leaf_col[leaf]]]
+    vec = None
+    stack = {}
+    for typ, node, flags, st, lb, n_pre, n_post in ops:
+        if typ == 0:                                        # LEAVES
+            assert n_pre >= 1 and n_post == 0
+            vec = column(leaves[lb]).copy()
+            for q in range(1, n_pre):
+                vec = vec * column(leaves[lb + q])
+        elif typ == 1:                                      # GEMM
+            assert vec is not None
+            acc = mats[node] @ vec[:mf + 1]
+            vec = None                                      # consumed
+            if n_pre:
+                assert not (flags & 1), "leaves before the first internal child only"
+                pre = column(leaves[lb]).copy()
+                for q in range(1, n_pre):
+                    pre = pre * column(leaves[lb + q])
+                acc = pre * acc
+            if flags & 1:
+                assert 0 <= st < depth
+                acc = stack.pop(st) * acc
+            for q in range(n_post):
+                acc = acc * column(leaves[lb + n_pre + q])
+            if flags & 2:
+                assert st not in stack and 0 <= st < depth
+                stack[st] = acc
+            else:
+                vec = acc
+        else:                                               # ROOT
+            assert vec is not None and not stack
+            return vec[1:mrf + 1]
+    raise AssertionError("no ROOT op")
 
 
 def interpret(tree, ops, n_slots, counts_row, lambdas, mf, mrf):
@@ -125,6 +175,36 @@ def test_schedule_reproduces_inference_prune(name, n_slots):
         got = interpret(tree, ops, n_slots, row, lam, mf, mrf)
         want = orc.inference_prune(tree, row, lam, mf, mrf)
         np.testing.assert_allclose(got, want, rtol=1e-12, atol=0)
+
+
+@pytest.mark.parametrize("name", sorted(TREES))
+def test_program_reproduces_inference_prune(name):
+    tree = hostio.flatten_tree(hostio.parse_newick(TREES[name]))
+    ops, leaves, depth = plan_program(tree)
+    assert ops[-1, 0] == 2 and (ops[:, 0] == 2).sum() == 1
+    internal_children = sum(1 for v in range(tree.n_nodes - 1) if tree.leaf_col[v] < 0)
+    assert (ops[:, 0] == 1).sum() == internal_children
+    assert len(leaves) == tree.n_leaves and sorted(leaves) == [v for v in range(tree.n_nodes) if tree.leaf_col[v] >= 0]
+    assert ((ops[:, 2] & 2) != 0).sum() == ((ops[:, 2] & 1) != 0).sum(), "every parked product is popped"
+    expected_depth = {"cherry": 0, "abcd": 1, "caterpillar": 0, "tri": 1, "balanced16": 3}[name]
+    assert depth == expected_depth
+    rng = np.random.default_rng(3)
+    mf, mrf = 14, 10
+    lam = [0.04]
+    for _ in range(3):
+        row = rng.integers(0, 7, tree.n_leaves).astype(np.int32)
+        got = interpret_program(tree, ops, leaves, depth, row, lam, mf, mrf)
+        want = orc.inference_prune(tree, row, lam, mf, mrf)
+        np.testing.assert_allclose(got, want, rtol=1e-12, atol=0)
+
+
+def test_program_on_config5_tree():
+    newick = synth.random_ultrametric_newick(100, 12345)
+    tree = hostio.flatten_tree(hostio.parse_newick(newick))
+    ops, leaves, depth = plan_program(tree)
+    assert (ops[:, 0] == 1).sum() == 98 and len(leaves) == 100
+    assert depth <= 4, "the parked stack of the benchmark tree fits tensor memory (4 entries at N = 151, three groups)"
+    assert (ops[(ops[:, 0] == 1), 5] == 0).all(), "binary tree: leaves are always multiplied after the internal child"
 
 
 def test_schedule_on_config5_tree_spills_at_most_once_with_four_slots():
