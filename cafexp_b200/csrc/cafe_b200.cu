@@ -60,6 +60,7 @@ cudaError_t dev_alloc(T** p, size_t n, bool zero = false)
 
 constexpr int FAMILY_PAD = 96;          // count rows are padded (zeros) to whole tiles of 16, 32 and 48 families
 constexpr int MAX_PARTIALS = 1024;
+constexpr int TIMING_HISTORY = 64;
 
 // Offsets (bytes) of the per-evaluation parameter block: one pinned host image, one device copy per shard, moved
 // with a single cudaMemcpyAsync.  Small fixed-size tables first, the pow(coeff, j) rows last, so that only the
@@ -111,8 +112,20 @@ struct Shard {
     double* h_result = nullptr;         // pinned [2]
     int* h_range = nullptr;             // pinned [2]
     cudaEvent_t staged = nullptr;       // H2D copy of the last parameter block has been consumed
-    cudaEvent_t ev[5] = {nullptr, nullptr, nullptr, nullptr, nullptr};
-    bool ev_valid[5] = {false, false, false, false, false};
+    // phase events of the last TIMING_HISTORY calls (a ring: callers that enqueue several evaluations without
+    // synchronising read their durations afterwards, cafe_b200_timing_history); ev / ev_valid point at the current slot
+    cudaEvent_t hist_ev[TIMING_HISTORY][5] = {};
+    bool hist_valid[TIMING_HISTORY][5] = {};
+    int hist_cur = 0;
+    cudaEvent_t* ev = hist_ev[0];
+    bool* ev_valid = hist_valid[0];
+    void next_timing_slot()
+    {
+        hist_cur = (hist_cur + 1) % TIMING_HISTORY;
+        ev = hist_ev[hist_cur];
+        ev_valid = hist_valid[hist_cur];
+        for (int i = 0; i < 5; ++i) ev_valid[i] = false;
+    }
 };
 
 struct cafe_b200_ctx {
@@ -214,6 +227,9 @@ bool plan_prune(cafe_b200_ctx* c, int smem_limit)
     std::vector<PruneGeom> candidates;
     if (c->n <= 256) {
         const int rb = (c->n + 31) / 32;
+        // three consumer groups where 160 registers per thread hold the accumulators (row blocks <= 5): 40 KB ring stages
+        // (half the barrier traffic; measured 0.785 vs 0.771-0.782 of the DMMA peak with 20 KB stages), else 20 KB stages
+        if (rb <= 5) candidates.push_back({rb, 4, 3, 4, 1});
         if (rb <= 5) candidates.push_back({rb, 4, 3, 2, 2});
         candidates.push_back({rb, 4, 2, 2, 2});
     }
@@ -246,7 +262,7 @@ bool plan_prune(cafe_b200_ctx* c, int smem_limit)
             int stages = (smem_limit - fixed) / stage;
             stages = std::min(stages, MAX_RING_STAGES);
             if (forced_stages > 0) stages = std::min(stages, forced_stages);
-            const int min_stages = (g.gw == 8) ? 2 : 3;
+            const int min_stages = 2;
             if (stages < min_stages) continue;
             c->geom = g;
             c->n_stages = stages;
@@ -435,6 +451,7 @@ int shard_build(cafe_b200_ctx* c, Shard* s)
 {
     CUDA_TRY(c, cudaSetDevice(s->device));
     cudaStream_t st = s->stream;
+    s->next_timing_slot();
     CUDA_TRY(c, cudaMemcpyAsync(s->d_param, c->h_param, c->param_used, cudaMemcpyHostToDevice, st));
     CUDA_TRY(c, cudaEventRecord(s->staged, st));
     CUDA_TRY(c, cudaEventRecord(s->ev[0], st));
@@ -673,7 +690,8 @@ void destroy_shard(Shard* s)
     if (s->h_result) cudaFreeHost(s->h_result);
     if (s->h_range) cudaFreeHost(s->h_range);
     if (s->staged) cudaEventDestroy(s->staged);
-    for (auto& e : s->ev) if (e) cudaEventDestroy(e);
+    for (auto& slot : s->hist_ev)
+        for (auto& e : slot) if (e) cudaEventDestroy(e);
     if (s->own_stream) cudaStreamDestroy(s->own_stream);
     delete s;
 }
@@ -790,7 +808,8 @@ int cafe_b200_create_multi(cafe_b200_ctx** out, const cafe_b200_tree* tree, cons
         s->stream = s->own_stream;
         CREATE_TRY(cudaEventCreateWithFlags(&s->staged, cudaEventDisableTiming));
         CREATE_TRY(cudaEventRecord(s->staged, s->stream));
-        for (auto& e : s->ev) CREATE_TRY(cudaEventCreate(&e));
+        for (auto& slot : s->hist_ev)
+            for (auto& e : slot) CREATE_TRY(cudaEventCreate(&e));
     }
 
     if (!plan_prune(c, smem_limit)) { g_create_error = "not enough shared memory for the pruning kernel at this matrix size / tree"; cafe_b200_destroy(c); return CAFE_B200_ERR_LIMIT; }
@@ -1244,6 +1263,28 @@ int cafe_b200_last_timings(const cafe_b200_ctx* c, double* ms4)
         cudaGetLastError();
     }
     return CAFE_B200_OK;
+}
+
+int cafe_b200_timing_history(const cafe_b200_ctx* c, int n, double* ms)
+{
+    if (!c || !ms || n < 1) return CAFE_B200_ERR_ARG;
+    n = std::min(n, TIMING_HISTORY);
+    for (int j = 0; j < n; ++j) {
+        double* row = ms + 4 * j;
+        row[0] = row[1] = row[2] = row[3] = 0.0;
+        for (const Shard* s : c->shards) {
+            const int slot = ((s->hist_cur - j) % TIMING_HISTORY + TIMING_HISTORY) % TIMING_HISTORY;
+            const cudaEvent_t* ev = s->hist_ev[slot];
+            const bool* ok = s->hist_valid[slot];
+            float t = 0.f;
+            if (ok[0] && ok[1] && cudaEventElapsedTime(&t, ev[0], ev[1]) == cudaSuccess) row[0] = std::max(row[0], (double)t);
+            if (ok[1] && ok[2] && cudaEventElapsedTime(&t, ev[1], ev[2]) == cudaSuccess) row[1] = std::max(row[1], (double)t);
+            if (ok[2] && ok[3] && cudaEventElapsedTime(&t, ev[2], ev[3]) == cudaSuccess) row[2] = std::max(row[2], (double)t);
+            if (ok[1] && ok[4] && cudaEventElapsedTime(&t, ev[1], ev[4]) == cudaSuccess) row[3] = std::max(row[3], (double)t);
+            cudaGetLastError();
+        }
+    }
+    return n;
 }
 
 int cafe_b200_describe(const cafe_b200_ctx* c, char* out, int cap)

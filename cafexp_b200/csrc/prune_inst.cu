@@ -1,7 +1,8 @@
 // One translation unit per row-block count: nvcc -DCAFE_RB=<1..8> prune_inst.cu (see __graft_entry__.build()).
 // Geometries compiled (gw, ng, cps, pw):
 //   every RB      (4, 2, 2, 2)   two consumer groups                                  matrix size <= 256
-//   RB <= 5       (4, 3, 2, 2)   three consumer groups (the default where it fits)    matrix size <= 160
+//   RB <= 5       (4, 3, 4, 1)   three consumer groups, 40 KB ring stages (the default where it fits)   matrix size <= 160
+//   RB <= 5       (4, 3, 2, 2)   three consumer groups, 20 KB ring stages
 //   RB >= 5       (8, 1, 1, 1)   one group of eight warps, 64*RB rows                 matrix size 257 .. 512
 //   RB == 5       a few more, selected by the CAFE_B200_GEOM environment variable (measurements in profiles/)
 #include <cstdio>
@@ -45,6 +46,7 @@ cudaError_t CAFE_CAT(prune_launch_rb, CAFE_RB)(const PruneGeom& g, const PrunePa
 {
     GEOM(4, 2, 2, 2)
 #if CAFE_RB <= 5
+    GEOM(4, 3, 4, 1)
     GEOM(4, 3, 2, 2)
 #endif
 #if CAFE_RB >= 5
@@ -52,9 +54,9 @@ cudaError_t CAFE_CAT(prune_launch_rb, CAFE_RB)(const PruneGeom& g, const PrunePa
 #endif
 #if CAFE_RB == 5
     GEOM(4, 3, 2, 1)
-    GEOM(4, 3, 1, 2)
+    GEOM(4, 3, 3, 2)
+    GEOM(4, 3, 4, 2)
     GEOM(4, 2, 4, 2)
-    GEOM(4, 2, 2, 1)
 #endif
     return cudaErrorInvalidConfiguration;
 }
@@ -65,10 +67,11 @@ bool prune_geometry_compiled(const PruneGeom& g)
     if (g.rb < 1 || g.rb > 8) return false;
     if (g.gw == 4 && g.ng == 2 && g.cps == 2 && g.pw == 2) return true;
     if (g.gw == 4 && g.ng == 3 && g.cps == 2 && g.pw == 2) return g.rb <= 5;
+    if (g.gw == 4 && g.ng == 3 && g.cps == 4 && g.pw == 1) return g.rb <= 5;
     if (g.gw == 8 && g.ng == 1 && g.cps == 1 && g.pw == 1) return g.rb >= 5;
     if (g.rb == 5 && g.gw == 4)
-        return (g.ng == 3 && g.cps == 2 && g.pw == 1) || (g.ng == 3 && g.cps == 1 && g.pw == 2) || (g.ng == 2 && g.cps == 4 && g.pw == 2) ||
-               (g.ng == 2 && g.cps == 2 && g.pw == 1);
+        return (g.ng == 3 && g.cps == 2 && g.pw == 1) || (g.ng == 3 && g.cps == 3 && g.pw == 2) || (g.ng == 3 && g.cps == 4 && g.pw == 2) ||
+               (g.ng == 2 && g.cps == 4 && g.pw == 2);
     return false;
 }
 #endif

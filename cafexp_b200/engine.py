@@ -30,7 +30,7 @@ EXPORTS = [
     "cafe_b200_eval", "cafe_b200_eval_device", "cafe_b200_reconstruct", "cafe_b200_build_matrices", "cafe_b200_matrix_size",
     "cafe_b200_prune_roots", "cafe_b200_launch_count", "cafe_b200_last_timings", "cafe_b200_root_max", "cafe_b200_pvalues",
     "cafe_b200_branch_probabilities", "cafe_b200_create_multi", "cafe_b200_n_devices", "cafe_b200_alloc_pinned", "cafe_b200_free_pinned",
-    "cafe_b200_set_families_ex", "cafe_b200_plan_program", "cafe_b200_describe", "cafe_b200_fetch_category_likelihoods",
+    "cafe_b200_set_families_ex", "cafe_b200_plan_program", "cafe_b200_describe", "cafe_b200_fetch_category_likelihoods", "cafe_b200_timing_history",
 ]
 
 _dp = C.POINTER(C.c_double)
@@ -83,6 +83,8 @@ def load_library():
     L.cafe_b200_plan_program.argtypes = [C.POINTER(_Tree), _ip, C.c_int, _ip, _ip, C.c_int, _ip, _ip]
     L.cafe_b200_fetch_category_likelihoods.restype = C.c_int
     L.cafe_b200_fetch_category_likelihoods.argtypes = [C.c_void_p, C.c_int, _dp]
+    L.cafe_b200_timing_history.restype = C.c_int
+    L.cafe_b200_timing_history.argtypes = [C.c_void_p, C.c_int, _dp]
     L.cafe_b200_describe.restype = C.c_int
     L.cafe_b200_describe.argtypes = [C.c_void_p, C.c_char_p, C.c_int]
     L.cafe_b200_destroy.argtypes = [C.c_void_p]
@@ -242,8 +244,10 @@ class Engine:
         lam = np.ascontiguousarray(np.atleast_2d(np.asarray(lambdas, np.float64)))
         return lam, lam.shape[0], lam.shape[1]
 
-    def infer(self, lambdas, prior, cat_probs=None, mode=BASE_LOGMAX, want_family=True, want_cat=True, failed_cap=1024):
-        """One likelihood evaluation.  lambdas: [k][n_lambdas] raw lambda_i*multiplier_k."""
+    def infer(self, lambdas, prior, cat_probs=None, mode=BASE_LOGMAX, want_family=True, want_cat=True, failed_cap=1024,
+              out_family=None, out_cat=None):
+        """One likelihood evaluation.  lambdas: [k][n_lambdas] raw lambda_i*multiplier_k.
+        out_family / out_cat: caller-owned float64 arrays (e.g. page-locked) the per-family outputs are written to."""
         lam, k, nl = self._lams(lambdas)
         cp = np.ascontiguousarray(cat_probs if cat_probs is not None else np.ones(k), np.float64)
         pr = np.ascontiguousarray(prior, np.float64)
@@ -251,8 +255,12 @@ class Engine:
             raise ValueError("prior must have max_root_family_size entries")
         score = C.c_double()
         nf = C.c_int64()
-        fam = np.empty(self.n_families) if want_family else None
-        cat = np.empty((self.n_families, k)) if (want_cat and mode == GAMMA_LINSUM) else None
+        fam = (out_family if out_family is not None else np.empty(self.n_families)) if want_family else None
+        cat = (out_cat if out_cat is not None else np.empty((self.n_families, k))) if (want_cat and mode == GAMMA_LINSUM) else None
+        if fam is not None and (fam.dtype != np.float64 or fam.size < self.n_families or not fam.flags.c_contiguous):
+            raise ValueError("out_family must be a contiguous float64 array of n_families entries")
+        if cat is not None and (cat.dtype != np.float64 or cat.size < self.n_families * k or not cat.flags.c_contiguous):
+            raise ValueError("out_cat must be a contiguous float64 array of n_families x k entries")
         fidx = np.full(failed_cap, -1, np.int64)
         rc = self._lib.cafe_b200_eval(self._h, _d(lam), nl, _d(cp), k, _d(pr), mode, C.byref(score),
                                       _d(fam) if fam is not None else None, _d(cat) if cat is not None else None,
@@ -322,6 +330,12 @@ class Engine:
     @property
     def launches(self) -> int:
         return int(self._lib.cafe_b200_launch_count(self._h))
+
+    def timing_history_ms(self, n: int) -> np.ndarray:
+        """[m][4] device times (matrix build, prune, reduce, reconstruct) of the most recent m <= n calls, newest first."""
+        ms = np.zeros((n, 4))
+        m = self._lib.cafe_b200_timing_history(self._h, n, _d(ms))
+        return ms[:max(m, 0)]
 
     def last_timings_ms(self) -> dict:
         ms = np.zeros(4)

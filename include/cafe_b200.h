@@ -236,6 +236,11 @@ int64_t cafe_b200_launch_count(const cafe_b200_ctx* ctx);
  * [3] reconstruction.  Valid after the call returned (it synchronises). */
 int  cafe_b200_last_timings(const cafe_b200_ctx* ctx, double* ms4);
 
+/* The same for the most recent n calls, newest first: ms [n][4] (a caller that enqueues several cafe_b200_eval_device
+ * calls without synchronising reads their kernel durations afterwards).  Returns the number of rows filled (<= 64);
+ * call after the work has completed. */
+int  cafe_b200_timing_history(const cafe_b200_ctx* ctx, int n, double* ms);
+
 #ifdef __cplusplus
 }
 #endif

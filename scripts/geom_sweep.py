@@ -30,7 +30,8 @@ def main():
     freq, rate, prior = bench.gamma_parameters()
     lams = np.ascontiguousarray(rate[:, None] * np.array([[bench.LAMBDA]]))
     flops = bench.algorithmic_flops_per_family_category(tree, bench.MF, bench.MRF) * bench.K * args.families
-    for geom in args.geoms.split():
+    for spec in args.geoms.split():
+        geom = spec
         if geom == "default":
             os.environ.pop("CAFE_B200_GEOM", None)
         else:
@@ -42,10 +43,10 @@ def main():
                     res = eng.infer(lams, prior, freq, engine.GAMMA_LINSUM, want_family=False, want_cat=False)
                     tm = eng.last_timings_ms()
                     best = min(best, tm["prune"])
-                print(json.dumps({"geom": geom, "prune_ms": round(best, 3), "build_ms": round(tm["matrix_build"], 3), "tflops": round(flops / best / 1e9, 3),
+                print(json.dumps({"geom": spec, "prune_ms": round(best, 3), "build_ms": round(tm["matrix_build"], 3), "tflops": round(flops / best / 1e9, 3),
                                   "frac": round(flops / best / 1e9 / args.peak, 4), "neg_lnl": res["score"], "describe": eng.describe()}), flush=True)
         except Exception as e:   # noqa: BLE001
-            print(json.dumps({"geom": geom, "error": str(e)}), flush=True)
+            print(json.dumps({"geom": spec, "error": str(e)}), flush=True)
 
 
 if __name__ == "__main__":

@@ -24,15 +24,19 @@ pytestmark = pytest.mark.gpu
 HARNESS = os.path.join(ROOT, "oracle", "_ref", "ref_harness_cuda")
 
 
-def run_harness(cmd, **kw):
+def run_harness(cmd, devices=None, **kw):
     argv = [HARNESS, cmd, "--cuda", "1"]
+    env = dict(os.environ)
+    env.pop("CAFE_B200_DEVICES", None)
+    if devices:
+        env["CAFE_B200_DEVICES"] = devices
     for key, val in kw.items():
         if val is None or val is False:
             continue
         argv.append("--" + key)
         if val is not True:
             argv.append(repr(val) if isinstance(val, float) else str(val))
-    res = subprocess.run(argv, capture_output=True, text=True)
+    res = subprocess.run(argv, capture_output=True, text=True, env=env)
     assert res.returncode == 0, res.stderr[-2000:]
     return json.loads([l for l in res.stdout.splitlines() if l.startswith("{\"")][-1])
 
@@ -145,3 +149,42 @@ def test_fit_through_reference_optimizer(files, name):
         assert rel(g, w) < 1e-6, (r["values"], want["values"])
     assert rel(fnum(r["score"]), fnum(want["score"])) < 1e-9
     assert r["evaluations"] == want["evaluations"] and r["iterations"] == want["iterations"]
+
+
+def _device_count():
+    from cafexp_b200 import engine
+    return engine.device_count()
+
+
+def test_lazy_results_are_what_the_reference_writes(files, mammal):
+    """model::results is materialised on demand by the drop-in (write_family_likelihoods); the harness dumps it after
+    several evaluations in a row: it must hold the LAST evaluation's values (reps = 3 here)."""
+    dump = os.path.join(files["dir"], "lazy.bin")
+    r = run_harness("eval", tree=files["tree"], fam=files["fam"], dump=dump, reps=3, **{"lambda": 0.002})
+    assert rel(fnum(r["score"]), fnum(mammal["meta"]["base_l002"]["score"])) < 1e-11
+    assert np.allclose(np.fromfile(dump, np.float64), mammal["gold"]["base_l002_lnl"], rtol=1e-11, atol=0)
+
+
+def test_drop_in_on_two_devices(files, mammal):
+    """CAFE_B200_DEVICES=0,1: the reference's single host thread drives both devices through one context
+    (cafe_b200_create_multi).  Evaluation with error model + reconstruction, and the joint lambda/alpha fit: identical
+    optimizer path (evaluations, iterations), parameters equal to the one-device fit."""
+    if _device_count() < 2:
+        pytest.skip("needs two visible CUDA devices")
+    name = "base_err_l01_recon"
+    gold = mammal["gold"]
+    dump, rec = os.path.join(files["dir"], "two.bin"), os.path.join(files["dir"], "two.rec")
+    r = run_harness("eval", devices="0,1", tree=files["tree"], fam=files["fam"], err=files["err"], dump=dump, recon=True, dumprecon=rec,
+                    **{"lambda": 0.01})
+    F = len(mammal["counts"])
+    assert rel(fnum(r["score"]), fnum(mammal["meta"][name]["score"])) < 1e-11
+    assert np.allclose(np.fromfile(dump, np.float64), gold[name + "_lnl"], rtol=1e-11, atol=0)
+    assert np.array_equal(np.fromfile(rec, np.int32).reshape(F, -1), gold[name + "_states"])
+    kw = {"tree": files["tree"], "fam": files["fam"], "seed": 10, "k": 4}
+    one = run_harness("fit", **kw)
+    two = run_harness("fit", devices="0,1", **kw)
+    assert one["devices"] == 1 and two["devices"] == 2
+    assert two["evaluations"] == one["evaluations"] and two["iterations"] == one["iterations"]
+    for a, b in zip(two["values"], one["values"]):
+        assert rel(a, b) < 1e-9
+    assert rel(fnum(two["score"]), fnum(one["score"])) < 1e-12
