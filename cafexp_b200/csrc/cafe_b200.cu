@@ -17,6 +17,7 @@
 #include "../../include/cafe_b200.h"
 
 #include <algorithm>
+#include <chrono>
 #include <climits>
 #include <cmath>
 #include <cstdio>
@@ -48,6 +49,14 @@ std::string g_create_error;
 struct NvtxRange {
     explicit NvtxRange(const char* name) { nvtxRangePushA(name); }
     ~NvtxRange() { nvtxRangePop(); }
+};
+
+// Adds the wall time of its scope to a counter.
+struct HostTimer {
+    double& acc;
+    std::chrono::steady_clock::time_point t0 = std::chrono::steady_clock::now();
+    explicit HostTimer(double& a) : acc(a) {}
+    ~HostTimer() { acc += std::chrono::duration<double>(std::chrono::steady_clock::now() - t0).count(); }
 };
 
 template <typename T>
@@ -163,6 +172,9 @@ struct cafe_b200_ctx {
     bool has_err = false;
     int64_t launches = 0;
     int64_t evals = 0;
+    // host wall time spent inside the library since create: [0] staging (keys, pow rows, program), [1] enqueueing copies
+    // and kernels, [2] waiting for the devices
+    double host_seconds[3] = {0.0, 0.0, 0.0};
     std::string error;
 };
 
@@ -363,6 +375,7 @@ int ensure_category_buffers(cafe_b200_ctx* c, int k)
 int stage_host(cafe_b200_ctx* c, const double* lambdas, int n_lambdas, int k, const double* cat_probs, const double* prior, int n_prior)
 {
     NvtxRange r("cafe_b200: stage keys");
+    HostTimer timer(c->host_seconds[0]);
     if (n_lambdas < c->tree.n_lambdas) return fail(c, CAFE_B200_ERR_ARG, "n_lambdas smaller than the tree's lambda indices");
     for (int i = 0; i < k * n_lambdas; ++i)
         if (!std::isfinite(lambdas[i]) || lambdas[i] < 0 || lambdas[i] * 1e9 >= 9.2e18)
@@ -409,7 +422,7 @@ int stage_host(cafe_b200_ctx* c, const double* lambdas, int n_lambdas, int k, co
     }
     // pow(coeff, j) rows from the host libm (src/probability.cpp:125): n_keys * N calls, threaded when there are many
     const int n = c->n;
-    #pragma omp parallel for schedule(static) if ((size_t)n_keys * n > 20000) num_threads(8)
+    #pragma omp parallel for schedule(static) if ((size_t)n_keys * n > 4000) num_threads(8)
     for (int key = 0; key < n_keys; ++key) {
         const double coeff = h_keys[key].coeff;
         double* pw = h_powc + (size_t)key * n;
@@ -481,6 +494,7 @@ int stage_and_build(cafe_b200_ctx* c, const double* lambdas, int n_lambdas, int 
     int rc = stage_host(c, lambdas, n_lambdas, k, cat_probs, prior, n_prior);
     if (rc) return rc;
     NvtxRange r("cafe_b200: build matrices");
+    HostTimer timer(c->host_seconds[1]);
     for (Shard* s : c->shards) {
         rc = shard_build(c, s);
         if (rc) return rc;
@@ -649,6 +663,7 @@ int enqueue_eval(cafe_b200_ctx* c, const double* lambdas, int n_lambdas, const d
     rc = stage_and_build(c, lambdas, n_lambdas, k, cat_probs, prior, c->mrf);
     if (rc) return rc;
     NvtxRange r("cafe_b200: prune + reduce");
+    HostTimer timer(c->host_seconds[1]);
     for (Shard* s : c->shards) {
         CUDA_TRY(c, cudaSetDevice(s->device));
         rc = launch_prune(c, s, k, mode, nullptr);
@@ -671,6 +686,7 @@ int enqueue_eval(cafe_b200_ctx* c, const double* lambdas, int n_lambdas, const d
 
 int sync_all(cafe_b200_ctx* c)
 {
+    HostTimer timer(c->host_seconds[2]);
     for (Shard* s : c->shards) {
         CUDA_TRY(c, cudaSetDevice(s->device));
         CUDA_TRY(c, cudaStreamSynchronize(s->stream));
@@ -1262,6 +1278,13 @@ int cafe_b200_last_timings(const cafe_b200_ctx* c, double* ms4)
         if (s->ev_valid[1] && s->ev_valid[4] && cudaEventElapsedTime(&ms, s->ev[1], s->ev[4]) == cudaSuccess) ms4[3] = std::max(ms4[3], (double)ms);
         cudaGetLastError();
     }
+    return CAFE_B200_OK;
+}
+
+int cafe_b200_host_seconds(const cafe_b200_ctx* c, double* s3)
+{
+    if (!c || !s3) return CAFE_B200_ERR_ARG;
+    for (int i = 0; i < 3; ++i) s3[i] = c->host_seconds[i];
     return CAFE_B200_OK;
 }
 

@@ -30,7 +30,7 @@ EXPORTS = [
     "cafe_b200_eval", "cafe_b200_eval_device", "cafe_b200_reconstruct", "cafe_b200_build_matrices", "cafe_b200_matrix_size",
     "cafe_b200_prune_roots", "cafe_b200_launch_count", "cafe_b200_last_timings", "cafe_b200_root_max", "cafe_b200_pvalues",
     "cafe_b200_branch_probabilities", "cafe_b200_create_multi", "cafe_b200_n_devices", "cafe_b200_alloc_pinned", "cafe_b200_free_pinned",
-    "cafe_b200_set_families_ex", "cafe_b200_plan_program", "cafe_b200_describe", "cafe_b200_fetch_category_likelihoods", "cafe_b200_timing_history",
+    "cafe_b200_set_families_ex", "cafe_b200_plan_program", "cafe_b200_describe", "cafe_b200_fetch_category_likelihoods", "cafe_b200_timing_history", "cafe_b200_host_seconds",
 ]
 
 _dp = C.POINTER(C.c_double)
@@ -85,6 +85,8 @@ def load_library():
     L.cafe_b200_fetch_category_likelihoods.argtypes = [C.c_void_p, C.c_int, _dp]
     L.cafe_b200_timing_history.restype = C.c_int
     L.cafe_b200_timing_history.argtypes = [C.c_void_p, C.c_int, _dp]
+    L.cafe_b200_host_seconds.restype = C.c_int
+    L.cafe_b200_host_seconds.argtypes = [C.c_void_p, _dp]
     L.cafe_b200_describe.restype = C.c_int
     L.cafe_b200_describe.argtypes = [C.c_void_p, C.c_char_p, C.c_int]
     L.cafe_b200_destroy.argtypes = [C.c_void_p]
@@ -336,6 +338,12 @@ class Engine:
         ms = np.zeros((n, 4))
         m = self._lib.cafe_b200_timing_history(self._h, n, _d(ms))
         return ms[:max(m, 0)]
+
+    def host_seconds(self) -> dict:
+        """Host wall time spent inside the library since create."""
+        s3 = np.zeros(3)
+        self._lib.cafe_b200_host_seconds(self._h, _d(s3))
+        return {"staging": s3[0], "enqueue": s3[1], "wait": s3[2]}
 
     def last_timings_ms(self) -> dict:
         ms = np.zeros(4)

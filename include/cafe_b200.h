@@ -225,6 +225,10 @@ int  cafe_b200_plan_schedule(const cafe_b200_tree* tree, int n_slots, int* ops_o
 int  cafe_b200_plan_program(const cafe_b200_tree* tree, int* ops_out, int cap, int* n_ops, int* leaves_out, int leaves_cap,
                             int* n_leaf_refs, int* depth);
 
+/* Host wall time (seconds) spent inside the library since create: [0] staging the evaluation parameters (key
+ * quantisation, pow rows from libm, the program), [1] enqueueing copies and kernels, [2] waiting for the devices. */
+int  cafe_b200_host_seconds(const cafe_b200_ctx* ctx, double* s3);
+
 /* Human-readable description of the launch geometry chosen for this context (groups, ring, tensor-memory use). */
 int  cafe_b200_describe(const cafe_b200_ctx* ctx, char* out, int cap);
 

@@ -3,6 +3,7 @@
 #include "cuda_models.h"
 
 #include <algorithm>
+#include <chrono>
 #include <cmath>
 #include <numeric>
 #include <random>
@@ -91,8 +92,20 @@ cuda_bridge::~cuda_bridge()
     release();
 }
 
+std::vector<double> cuda_bridge::host_seconds() const
+{
+    double lib[3] = {0.0, 0.0, 0.0};
+    if (_ctx) cafe_b200_host_seconds(_ctx, lib);
+    return {_bind_seconds, _eval_call_seconds, _lib_seconds_before[0] + lib[0], _lib_seconds_before[1] + lib[1], _lib_seconds_before[2] + lib[2]};
+}
+
 void cuda_bridge::release()
 {
+    if (_ctx) {
+        double lib[3] = {0.0, 0.0, 0.0};
+        cafe_b200_host_seconds(_ctx, lib);
+        for (int i = 0; i < 3; ++i) _lib_seconds_before[i] += lib[i];
+    }
     if (_ctx) cafe_b200_destroy(_ctx);
     _ctx = nullptr;
     cafe_b200_free_pinned(_h_family_lnl);
@@ -137,12 +150,13 @@ std::vector<int> cuda_bridge::devices_from_environment()
 
 int cuda_bridge::device_count() const { return _ctx ? cafe_b200_n_devices(_ctx) : 0; }
 
-// Counts of a spread of at most 64 rows: cheap next to an evaluation (a full pass costs F x leaves map look-ups),
-// enough to notice a bound vector that was edited in place.
+// Counts of a spread of rows, about 256 look-ups in all (a few microseconds; a full pass costs F x leaves string-keyed
+// map look-ups, milliseconds to seconds): enough to notice a bound vector that was edited in place.
 size_t cuda_bridge::fingerprint(const std::vector<gene_family>& families) const
 {
     size_t h = 1469598103934665603ull;
-    const size_t n = families.size(), step = std::max<size_t>(1, n / 64);
+    const size_t n = families.size(), rows = std::max<size_t>(2, 256 / std::max<size_t>(1, _leaves.size()));
+    const size_t step = std::max<size_t>(1, n / rows);
     for (size_t i = 0; i < n; i += step)
         for (const clade* leaf : _leaves) h = (h ^ (size_t)families[i].get_species_size(leaf->get_taxon_name())) * 1099511628211ull;
     return h;
@@ -151,14 +165,21 @@ size_t cuda_bridge::fingerprint(const std::vector<gene_family>& families) const
 void cuda_bridge::bind(const std::vector<gene_family>& families)
 {
     if (_ctx && _bound == &families && _bound_size == families.size() && _bound_fingerprint == fingerprint(families)) return;
+    const auto t0 = std::chrono::steady_clock::now();
     const size_t nl = _leaves.size();
     std::vector<int> rows(families.size() * nl);
-    for (size_t i = 0; i < families.size(); ++i)
-        for (size_t l = 0; l < nl; ++l) rows[i * nl + l] = families[i].get_species_size(_leaves[l]->get_taxon_name());
+    std::vector<std::string> names(nl);
+    for (size_t l = 0; l < nl; ++l) names[l] = _leaves[l]->get_taxon_name();
+    // F x leaves look-ups in each family's string-keyed map: spread over the host threads the reference's own loops use
+    const long n_fam = (long)families.size();
+#pragma omp parallel for schedule(static) if (n_fam * (long)nl > 100000)
+    for (long i = 0; i < n_fam; ++i)
+        for (size_t l = 0; l < nl; ++l) rows[(size_t)i * nl + l] = families[i].get_species_size(names[l]);
     bind_rows(rows, families.size());
     _bound = &families;
     _bound_size = families.size();
     _bound_fingerprint = fingerprint(families);
+    _bind_seconds += std::chrono::duration<double>(std::chrono::steady_clock::now() - t0).count();
 }
 
 void cuda_bridge::bind_rows(const std::vector<int>& rows, size_t n_rows)
@@ -260,9 +281,11 @@ long cuda_bridge::evaluate(const std::vector<double>& lambdas, const std::vector
     static_assert(sizeof(long long) == sizeof(int64_t), "64-bit indices");
     // only the per-family lnL comes back with every evaluation (the caller sums it in family order); the category
     // likelihoods stay on the device until somebody asks (category_likelihoods())
+    const auto t0 = std::chrono::steady_clock::now();
     check(cafe_b200_eval(_ctx, lambdas.data(), (int)_order.size(), cat_probs.data(), k, prior.data(), mode, &neg_lnl, _h_family_lnl, nullptr,
                          &n_failed, reinterpret_cast<int64_t*>(_failed_idx.data()), (int64_t)_failed_idx.size()),
           "cafe_b200_eval");
+    _eval_call_seconds += std::chrono::duration<double>(std::chrono::steady_clock::now() - t0).count();
     _last_k = mode == CAFE_B200_GAMMA_LINSUM ? k : 0;
     _cat_lk_fetched = false;
     ++_evaluations;

@@ -99,6 +99,9 @@ public:
     //! device time (CUDA events: matrix build + pruning + reduction) and number of evaluate() calls so far
     double device_seconds() const { return _device_seconds; }
     long evaluations() const { return _evaluations; }
+    //! host wall time so far: [0] bind (flatten + de-duplicate + create the context), [1] inside cafe_b200_eval, of which
+    //! [2] staging, [3] enqueueing, [4] waiting for the devices
+    std::vector<double> host_seconds() const;
 
     //! CUDA ordinals from CAFE_B200_DEVICES / CAFE_B200_DEVICE (see above).
     static std::vector<int> devices_from_environment();
@@ -127,6 +130,8 @@ private:
     std::vector<long long> _failed_idx;
     double _device_seconds = 0.0;
     long _evaluations = 0;
+    double _bind_seconds = 0.0, _eval_call_seconds = 0.0;
+    double _lib_seconds_before[3] = {0.0, 0.0, 0.0};     // library counters of contexts already destroyed
 
     void check(int rc, const char* what) const;
     size_t fingerprint(const std::vector<gene_family>& families) const;

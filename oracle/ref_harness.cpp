@@ -460,12 +460,14 @@ int cmd_fit(const args_t& a)
     std::unique_ptr<inference_optimizer_scorer> scorer(m->get_lambda_optimizer(s.data));
     if (!scorer) throw std::runtime_error("nothing to optimise");
     struct counting : optimizer_scorer {
-        inference_optimizer_scorer* inner; int evals = 0; double seconds = 0;
+        inference_optimizer_scorer* inner; int evals = 0; double seconds = 0, first = 0;
         std::vector<double> initial_guesses() override { return inner->initial_guesses(); }
         double calculate_score(const double* v) override {
             auto t0 = std::chrono::steady_clock::now();
             double r = inner->calculate_score(v); ++evals;
-            seconds += std::chrono::duration<double>(std::chrono::steady_clock::now() - t0).count();
+            const double dt = std::chrono::duration<double>(std::chrono::steady_clock::now() - t0).count();
+            seconds += dt;
+            if (evals == 1) first = dt;         // includes one-time set-up (de-duplication; for the CUDA models context creation + upload)
             return r;
         }
     } cs; cs.inner = scorer.get();
@@ -478,13 +480,19 @@ int cmd_fit(const args_t& a)
     printf("{"); print_setup(s);
     printf("\"model\": \"%s\", ", m->name().c_str()); jarr("values", result.values);
     printf(", \"score\": "); jnum(result.score);
-    printf(", \"iterations\": %d, \"evaluations\": %d, \"seconds\": %.6f, \"seconds_in_score\": %.6f", result.num_iterations, cs.evals, dt, cs.seconds);
+    printf(", \"iterations\": %d, \"evaluations\": %d, \"seconds\": %.6f, \"seconds_in_score\": %.6f, \"first_evaluation_seconds\": %.6f", result.num_iterations,
+           cs.evals, dt, cs.seconds, cs.first);
 #ifdef WITH_CUDA_MODELS
     {
         cuda_bridge* br = nullptr;
         if (auto cb = dynamic_cast<cuda_base_model*>(m)) br = &cb->bridge();
         if (auto cg = dynamic_cast<cuda_gamma_model*>(m)) br = &cg->bridge();
-        if (br) printf(", \"devices\": %d, \"device_evaluations\": %ld, \"device_seconds\": %.6f", br->device_count(), br->evaluations(), br->device_seconds());
+        if (br) {
+            const std::vector<double> hs = br->host_seconds();
+            printf(", \"devices\": %d, \"device_evaluations\": %ld, \"device_seconds\": %.6f, \"bind_seconds\": %.6f, \"eval_call_seconds\": %.6f, "
+                   "\"staging_seconds\": %.6f, \"enqueue_seconds\": %.6f, \"wait_seconds\": %.6f",
+                   br->device_count(), br->evaluations(), br->device_seconds(), hs[0], hs[1], hs[2], hs[3], hs[4]);
+        }
     }
 #endif
     printf("}\n");
