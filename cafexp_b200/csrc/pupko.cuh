@@ -66,6 +66,39 @@ struct PupkoSmem {
 
 constexpr int JC = PPS * 4;     // child sizes per ring stage
 
+// One child size j against four families of one parent-size row: val_f = v_f * m, strict '>' keeps the first maximum
+// (src/gene_family_reconstructor.cpp:96-105).  The four chains are written out with their own predicates so that the
+// multiply -> compare -> move latencies of different families overlap (left to the compiler every pair went through
+// one predicate register, i.e. one FP64 round trip per element: 35 % FP64 pipe use in round 1), and the update is a
+// predicated move rather than a select: selects all issue on the half-rate ALU pipe (three per element, the bound once the
+// latencies overlap), predicated moves can also go to the FMA pipe.
+__device__ __forceinline__ void maxprod4(double& b0, double& b1, double& b2, double& b3, int& a0, int& a1, int& a2, int& a3, double v0, double v1,
+                                         double v2, double v3, double m, int j)
+{
+    asm("{\n"
+        ".reg .pred p0, p1, p2, p3;\n"
+        ".reg .f64 t0, t1, t2, t3;\n"
+        "mul.rn.f64 t0, %8, %12;\n"
+        "mul.rn.f64 t1, %9, %12;\n"
+        "mul.rn.f64 t2, %10, %12;\n"
+        "mul.rn.f64 t3, %11, %12;\n"
+        "setp.gt.f64 p0, t0, %0;\n"
+        "setp.gt.f64 p1, t1, %1;\n"
+        "setp.gt.f64 p2, t2, %2;\n"
+        "setp.gt.f64 p3, t3, %3;\n"
+        "@p0 mov.f64 %0, t0;\n"
+        "@p1 mov.f64 %1, t1;\n"
+        "@p2 mov.f64 %2, t2;\n"
+        "@p3 mov.f64 %3, t3;\n"
+        "@p0 mov.s32 %4, %13;\n"
+        "@p1 mov.s32 %5, %13;\n"
+        "@p2 mov.s32 %6, %13;\n"
+        "@p3 mov.s32 %7, %13;\n"
+        "}\n"
+        : "+d"(b0), "+d"(b1), "+d"(b2), "+d"(b3), "+r"(a0), "+r"(a1), "+r"(a2), "+r"(a3)
+        : "d"(v0), "d"(v1), "d"(v2), "d"(v3), "d"(m), "r"(j));
+}
+
 template <int MB>
 __global__ void __launch_bounds__(PRUNE_THREADS, 1) pupko_kernel(const PupkoParams p)
 {
@@ -185,23 +218,20 @@ __global__ void __launch_bounds__(PRUNE_THREADS, 1) pupko_kernel(const PupkoPara
                     const uint32_t stage = pos % STAGES;
                     mbar_wait(&full_bar[stage], (pos / STAGES) & 1);
                     const double* m_stage = ring + (size_t)stage * L::STAGE_DOUBLES + lane;
+                    // Columns beyond max_family_size are zero in the transposed matrix (padding up to whole stages), so
+                    // their products are 0 (or NaN against a stale slot entry): neither beats a maximum that is >= 0
+                    // after j = 0 — no bounds test in the loop.
+                    static_assert(FPW == 4, "maxprod4 handles the four families of a warp");
                     #pragma unroll
                     for (int jj = 0; jj < JC; ++jj) {
                         const int j = ch * JC + jj;
-                        if (j <= p.mf) {
-                            double m[MB];
-                            #pragma unroll
-                            for (int i = 0; i < MB; ++i) m[i] = m_stage[jj * NR + 32 * i];
-                            #pragma unroll
-                            for (int fi = 0; fi < FPW; ++fi) {
-                                const double v = vsrc[fi * LDV + j];
-                                #pragma unroll
-                                for (int i = 0; i < MB; ++i) {
-                                    const double val = __dmul_rn(v, m[i]);
-                                    if (val > best[fi][i]) { best[fi][i] = val; arg[fi][i] = j; }
-                                }
-                            }
-                        }
+                        double m[MB];
+                        #pragma unroll
+                        for (int i = 0; i < MB; ++i) m[i] = m_stage[jj * NR + 32 * i];
+                        const double v0 = vsrc[0 * LDV + j], v1 = vsrc[1 * LDV + j], v2 = vsrc[2 * LDV + j], v3 = vsrc[3 * LDV + j];
+                        #pragma unroll
+                        for (int i = 0; i < MB; ++i)
+                            maxprod4(best[0][i], best[1][i], best[2][i], best[3][i], arg[0][i], arg[1][i], arg[2][i], arg[3][i], v0, v1, v2, v3, m[i], j);
                     }
                     __syncwarp();
                     if (lane == 0) mbar_arrive(&empty_bar[stage]);
