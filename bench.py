@@ -217,7 +217,8 @@ def workload_config(args, world):
     return {"workload": f"BASELINE.json configs[4]: synthetic {args.families} families x {N_LEAVES}-taxon ultrametric tree, Nmax={MF}, "
                         f"max_root_family_size={MRF}, gamma k={K} alpha={ALPHA}, lambda={LAMBDA}, uniform root prior",
             "families": args.families, "taxa": N_LEAVES, "matrix_size": MF + 1, "gamma_categories": K,
-            "parallelism": f"families sharded over {world} GPU(s), one 2-double NCCL allreduce per evaluation" if world > 1 else "1 GPU",
+            "parallelism": (f"families sharded over {world} GPU(s); per evaluation: transition matrices built once (1/{world} per rank) + NCCL all-gather over "
+                            f"NVLink, then one 2-double NCCL allreduce") if world > 1 else "1 GPU",
             "l2": "L2 flushed (256 MiB write) between timed steps", "seed": SEED}
 
 
@@ -376,6 +377,7 @@ def main():
     ap.add_argument("--no-e2e", action="store_true")
     ap.add_argument("--no-fit", action="store_true")
     ap.add_argument("--no-reconstruct", action="store_true")
+    ap.add_argument("--replicated-build", action="store_true", help="N > 1: every rank builds all transition matrices itself (round-1 behaviour)")
     ap.add_argument("--record-score", action="store_true", help="write the 1-GPU score of this workload to profiles/ (the N > 1 parity reference)")
     args = ap.parse_args()
     args.warmup = max(args.warmup, 0)
@@ -421,6 +423,9 @@ def main():
 
     from cafexp_b200 import sharded
     job = sharded.ShardedLikelihood(sharded.engine_local_eval(eng), result)     # shard evaluation + one 2-double allreduce
+    if world > 1 and not args.replicated_build:
+        # every transition matrix is built once, by one rank, and all-gathered over NVLink (instead of N redundant builds)
+        eng.set_build_partition(rank, world, sharded.nccl_matrix_gather())
 
     def step():
         job.enqueue(lams, prior, freq, engine.GAMMA_LINSUM)

@@ -39,6 +39,7 @@ struct MatrixBuildParams {
     int mf;            // columns kept: c <= mf
     int nr;            // padded rows
     int n_keys;
+    int key_first;     // this launch builds keys key_first .. key_first + gridDim.y - 1 (a slab, when the build is distributed)
     int lg_len;        // entries of the lgamma table (2 N + 2)
     const KeyParams* keys;      // [n_keys]
     const double* powc;         // [n_keys][n]  pow(coeff, j) from the host libm
@@ -59,7 +60,7 @@ __global__ void __launch_bounds__(MB_THREADS) bd_matrix_kernel(const MatrixBuild
     extern __shared__ double sm[];
     double* lg = sm;                       // [lg_len]
     double* pw = sm + p.lg_len;            // [n]
-    const int key = blockIdx.y;
+    const int key = p.key_first + blockIdx.y;
     const KeyParams kp = p.keys[key];
     for (int i = threadIdx.x; i < p.lg_len; i += MB_THREADS) lg[i] = p.lgamma_tab[i];
     for (int i = threadIdx.x; i < p.n; i += MB_THREADS) pw[i] = p.powc[(size_t)key * p.n + i];

@@ -121,6 +121,7 @@ struct Shard {
     double* h_result = nullptr;         // pinned [2]
     int* h_range = nullptr;             // pinned [2]
     cudaEvent_t staged = nullptr;       // H2D copy of the last parameter block has been consumed
+    cudaEvent_t built = nullptr;        // this shard's slab of matrices has been built and sent to its peers
     // phase events of the last TIMING_HISTORY calls (a ring: callers that enqueue several evaluations without
     // synchronising read their durations afterwards, cafe_b200_timing_history); ev / ev_valid point at the current slot
     cudaEvent_t hist_ev[TIMING_HISTORY][5] = {};
@@ -164,7 +165,14 @@ struct cafe_b200_ctx {
     unsigned char* h_param = nullptr;
     size_t h_param_bytes = 0;
     size_t param_used = 0;
-    int n_keys = 0;
+    int n_keys = 0;                     // unique (lambda, t) keys of the staged evaluation ...
+    int n_keys_padded = 0;              // ... rounded up to a whole number per builder when the build is distributed
+    // Distributed matrix build: every transition matrix is built ONCE, by one device, and delivered to the others over
+    // NVLink — inside a multi-device context by peer copies (below), across processes by a caller-supplied all-gather.
+    bool peer_ok = false;               // every pair of this context's devices can access each other
+    int ext_part = 0, ext_parts = 1;    // cafe_b200_set_build_partition
+    cafe_b200_gather_fn gather_cb = nullptr;
+    void* gather_user = nullptr;
     std::vector<double> err_host;       // last uploaded table
     double* h_err = nullptr;
     size_t h_err_cap = 0;
@@ -319,7 +327,7 @@ size_t leafrefs_per_category(const cafe_b200_ctx* c) { return std::max<size_t>(2
 ParamLayout make_layout(const cafe_b200_ctx* c, int k)
 {
     auto up = [](size_t x) { return (x + 15) & ~size_t(15); };
-    const size_t keys = (size_t)k * c->tree.n_nodes;
+    const size_t keys = (size_t)k * c->tree.n_nodes + 64;        // + padding keys of a distributed build
     ParamLayout l;
     size_t o = 0;
     l.prior = o; o = up(o + (size_t)c->n * sizeof(double));
@@ -346,7 +354,7 @@ int ensure_category_buffers(cafe_b200_ctx* c, int k)
     if (k > 64) return fail(c, CAFE_B200_ERR_LIMIT, "more than 64 rate categories");
     c->cap_k = 0;
     c->lay = make_layout(c, k);
-    const size_t keys = (size_t)k * c->tree.n_nodes;
+    const size_t keys = (size_t)k * c->tree.n_nodes + 64;
     for (Shard* s : c->shards) {
         CUDA_TRY(c, cudaSetDevice(s->device));
         CUDA_TRY(c, cudaStreamSynchronize(s->stream));
@@ -370,6 +378,17 @@ int ensure_category_buffers(cafe_b200_ctx* c, int k)
 // ------------------------------------------------------------------------------------------------------------------
 // per-evaluation staging
 // ------------------------------------------------------------------------------------------------------------------
+
+// How many builders share the matrix build of an evaluation with n_keys unique keys: the context's own devices (when
+// they can reach each other and the build is big enough to outweigh the exchange), or the external partition the
+// caller announced (cafe_b200_set_build_partition), else 1.
+int build_partitions(const cafe_b200_ctx* c, int n_keys)
+{
+    if (c->ext_parts > 1) return c->gather_cb ? c->ext_parts : 1;
+    const bool worth_it = (size_t)n_keys * c->n * c->n >= (size_t)4 << 20;         // >= ~0.3 ms of matrix build
+    if (c->shards.size() > 1 && c->peer_ok && worth_it && !getenv("CAFE_B200_REPLICATED_BUILD")) return (int)c->shards.size();
+    return 1;
+}
 
 // Quantise keys, de-duplicate, fill the pinned parameter block (once per call, shared by every shard).
 int stage_host(cafe_b200_ctx* c, const double* lambdas, int n_lambdas, int k, const double* cat_probs, const double* prior, int n_prior)
@@ -453,8 +472,21 @@ int stage_host(cafe_b200_ctx* c, const double* lambdas, int n_lambdas, int k, co
         }
         for (size_t i = n_leaf; i < leaf_row; ++i) h_leaf[(size_t)cat * leaf_row + i] = {0, 0};
     }
+    // distributed build: pad to a whole number of keys per builder with trivially "saturated" keys (one row of work)
+    const int builders = build_partitions(c, n_keys);
+    int padded = n_keys;
+    if (builders > 1) {
+        padded = (n_keys + builders - 1) / builders * builders;
+        for (int key = n_keys; key < padded; ++key) {
+            KeyParams kp;
+            kp.saturated = 1; kp.computable = 0; kp.log_alpha = 0.0; kp.coeff = 0.0;
+            h_keys[key] = kp;
+            std::fill(h_powc + (size_t)key * n, h_powc + (size_t)(key + 1) * n, 0.0);
+        }
+    }
     c->n_keys = n_keys;
-    c->param_used = c->lay.powc + (size_t)n_keys * c->n * sizeof(double);
+    c->n_keys_padded = padded;
+    c->param_used = c->lay.powc + (size_t)padded * c->n * sizeof(double);
     (void)slots;
     return CAFE_B200_OK;
 }
@@ -468,8 +500,13 @@ int shard_build(cafe_b200_ctx* c, Shard* s)
     CUDA_TRY(c, cudaMemcpyAsync(s->d_param, c->h_param, c->param_used, cudaMemcpyHostToDevice, st));
     CUDA_TRY(c, cudaEventRecord(s->staged, st));
     CUDA_TRY(c, cudaEventRecord(s->ev[0], st));
+    // the slab of keys this shard builds
+    const int builders = build_partitions(c, c->n_keys);
+    const int part = c->ext_parts > 1 ? c->ext_part : s->index;
+    const int per = builders > 1 ? c->n_keys_padded / builders : c->n_keys;
+    const int key_first = builders > 1 ? part * per : 0;
     MatrixBuildParams mp;
-    mp.n = c->n; mp.mf = c->mf; mp.nr = c->nr; mp.n_keys = c->n_keys; mp.lg_len = c->lg_len;
+    mp.n = c->n; mp.mf = c->mf; mp.nr = c->nr; mp.n_keys = c->n_keys_padded; mp.key_first = key_first; mp.lg_len = c->lg_len;
     mp.keys = reinterpret_cast<const KeyParams*>(s->d_param + c->lay.keys);
     mp.powc = reinterpret_cast<const double*>(s->d_param + c->lay.powc);
     mp.lgamma_tab = s->d_lgamma;
@@ -477,13 +514,31 @@ int shard_build(cafe_b200_ctx* c, Shard* s)
     const int entries = ((c->n + 31) / 32) * 32 * (c->mf + 1);
     int bx = (entries + MB_THREADS - 1) / MB_THREADS;
     // keep the whole launch near a few waves: many keys -> fewer blocks per key (grid-stride inside)
-    const int target = std::max(1, (8 * s->sm_count + c->n_keys - 1) / std::max(1, c->n_keys));
+    const int target = std::max(1, (8 * s->sm_count + per - 1) / std::max(1, per));
     bx = std::max(1, std::min(bx, target));
-    dim3 grid(bx, std::max(1, c->n_keys));
+    dim3 grid(bx, std::max(1, per));
     const size_t smem = ((size_t)c->lg_len + c->n) * sizeof(double);
     bd_matrix_kernel<<<grid, MB_THREADS, smem, st>>>(mp);
     CUDA_TRY(c, cudaGetLastError());
     c->launches++;
+    if (builders > 1) {
+        const size_t mp_off = (size_t)key_first * c->mp_stride, mp_cnt = (size_t)per * c->mp_stride;
+        const size_t mt_off = (size_t)key_first * c->mt_stride, mt_cnt = (size_t)per * c->mt_stride;
+        if (c->ext_parts > 1) {
+            // across processes: the caller's all-gather (NCCL on this stream) delivers every builder's slab everywhere
+            const int rc = c->gather_cb(c->gather_user, s->d_mp, mp_cnt * sizeof(double), s->d_mt, mt_cnt * sizeof(double), builders, (void*)st);
+            if (rc != 0) return fail(c, CAFE_B200_ERR_CUDA, "the matrix all-gather callback failed");
+        }
+        else {
+            // inside one context: push this shard's slab to every peer over NVLink (copy engines, stream-ordered after the build)
+            for (Shard* d : c->shards) {
+                if (d == s) continue;
+                CUDA_TRY(c, cudaMemcpyPeerAsync(d->d_mp + mp_off, d->device, s->d_mp + mp_off, s->device, mp_cnt * sizeof(double), st));
+                CUDA_TRY(c, cudaMemcpyPeerAsync(d->d_mt + mt_off, d->device, s->d_mt + mt_off, s->device, mt_cnt * sizeof(double), st));
+            }
+            CUDA_TRY(c, cudaEventRecord(s->built, st));
+        }
+    }
     CUDA_TRY(c, cudaEventRecord(s->ev[1], st));
     s->ev_valid[0] = s->ev_valid[1] = true;
     return CAFE_B200_OK;
@@ -498,6 +553,15 @@ int stage_and_build(cafe_b200_ctx* c, const double* lambdas, int n_lambdas, int 
     for (Shard* s : c->shards) {
         rc = shard_build(c, s);
         if (rc) return rc;
+    }
+    if (c->ext_parts <= 1 && c->n_keys_padded > 0 && build_partitions(c, c->n_keys) > 1) {
+        // every shard prunes only after every peer's slab has arrived in its buffers
+        for (Shard* s : c->shards) {
+            CUDA_TRY(c, cudaSetDevice(s->device));
+            for (Shard* o : c->shards)
+                if (o != s) CUDA_TRY(c, cudaStreamWaitEvent(s->stream, o->built, 0));
+            CUDA_TRY(c, cudaEventRecord(s->ev[1], s->stream));       // the build phase ends when the last slab is in
+        }
     }
     return CAFE_B200_OK;
 }
@@ -706,6 +770,7 @@ void destroy_shard(Shard* s)
     if (s->h_result) cudaFreeHost(s->h_result);
     if (s->h_range) cudaFreeHost(s->h_range);
     if (s->staged) cudaEventDestroy(s->staged);
+    if (s->built) cudaEventDestroy(s->built);
     for (auto& slot : s->hist_ev)
         for (auto& e : slot) if (e) cudaEventDestroy(e);
     if (s->own_stream) cudaStreamDestroy(s->own_stream);
@@ -823,6 +888,7 @@ int cafe_b200_create_multi(cafe_b200_ctx** out, const cafe_b200_tree* tree, cons
         CREATE_TRY(cudaStreamCreateWithFlags(&s->own_stream, cudaStreamNonBlocking));
         s->stream = s->own_stream;
         CREATE_TRY(cudaEventCreateWithFlags(&s->staged, cudaEventDisableTiming));
+        CREATE_TRY(cudaEventCreateWithFlags(&s->built, cudaEventDisableTiming));
         CREATE_TRY(cudaEventRecord(s->staged, s->stream));
         for (auto& slot : s->hist_ev)
             for (auto& e : slot) CREATE_TRY(cudaEventCreate(&e));
@@ -837,6 +903,19 @@ int cafe_b200_create_multi(cafe_b200_ctx** out, const cafe_b200_tree* tree, cons
     c->mt_stride = (size_t)c->kpanels * 4 * c->nr;      // columns padded to whole ring stages (zeros)
     plan_pupko(c, smem_limit);
 
+    if (c->shards.size() > 1) {
+        c->peer_ok = true;
+        for (Shard* a : c->shards)
+            for (Shard* b : c->shards) {
+                if (a == b) continue;
+                int can = 0;
+                if (cudaDeviceCanAccessPeer(&can, a->device, b->device) != cudaSuccess || !can) { c->peer_ok = false; continue; }
+                cudaSetDevice(a->device);
+                const cudaError_t e = cudaDeviceEnablePeerAccess(b->device, 0);
+                if (e != cudaSuccess && e != cudaErrorPeerAccessAlreadyEnabled) c->peer_ok = false;
+                cudaGetLastError();
+            }
+    }
     std::vector<double> lg(c->lg_len);
     for (int i = 0; i < c->lg_len; ++i) lg[i] = lgamma((double)i);           // src/probability.cpp:58-72 (table below 1024, libm above: same values)
     std::vector<int> internal_idx(nn, -1);
@@ -996,6 +1075,15 @@ int cafe_b200_plan_program(const cafe_b200_tree* tree, int* ops_out, int cap, in
         if (leaves_cap < (int)p.leaves.size()) return CAFE_B200_ERR_ARG;
         std::copy(p.leaves.begin(), p.leaves.end(), leaves_out);
     }
+    return CAFE_B200_OK;
+}
+
+int cafe_b200_set_build_partition(cafe_b200_ctx* c, int part, int n_parts, cafe_b200_gather_fn gather, void* user)
+{
+    if (!c) return CAFE_B200_ERR_ARG;
+    if (c->shards.size() != 1) return fail(c, CAFE_B200_ERR_ARG, "set_build_partition: single-device contexts only (a multi-device context distributes by itself)");
+    if (n_parts < 1 || part < 0 || part >= n_parts || n_parts > 64 || (n_parts > 1 && !gather)) return fail(c, CAFE_B200_ERR_ARG, "bad build partition");
+    c->ext_part = part; c->ext_parts = n_parts; c->gather_cb = gather; c->gather_user = user;
     return CAFE_B200_OK;
 }
 
@@ -1315,9 +1403,10 @@ int cafe_b200_describe(const cafe_b200_ctx* c, char* out, int cap)
     if (!c || !out || cap < 1) return CAFE_B200_ERR_ARG;
     snprintf(out, cap,
              "devices=%zu matrix=%d rows=%d geom(rb=%d,gw=%d,groups=%d,cps=%d,producers=%d) stages=%d smem=%d count_bytes=%d counts_in_smem=%d "
-             "program_in_smem=%d stack_depth=%d tmem_entries=%d tmem_cols=%d spill_entries=%d gemm_ops=%d ops=%zu",
+             "program_in_smem=%d peer_access=%d build_partitions=%d stack_depth=%d tmem_entries=%d tmem_cols=%d spill_entries=%d gemm_ops=%d ops=%zu",
              c->shards.size(), c->n, c->nr, c->geom.rb, c->geom.gw, c->geom.ng, c->geom.cps, c->geom.pw, c->n_stages, c->prune_smem, c->cnt_width,
-             c->cnt_smem_bytes > 0 ? 1 : 0, c->ops_smem_bytes > 0 ? 1 : 0, c->prog.depth, c->tmem_entries, c->tmem_cols, c->n_gspill, c->prog.n_gemm, c->prog.ops.size());
+             c->cnt_smem_bytes > 0 ? 1 : 0, c->ops_smem_bytes > 0 ? 1 : 0, c->peer_ok ? 1 : 0, c->ext_parts > 1 ? c->ext_parts : (c->peer_ok ? (int)c->shards.size() : 1),
+             c->prog.depth, c->tmem_entries, c->tmem_cols, c->n_gspill, c->prog.n_gemm, c->prog.ops.size());
     return CAFE_B200_OK;
 }
 

@@ -30,7 +30,7 @@ EXPORTS = [
     "cafe_b200_eval", "cafe_b200_eval_device", "cafe_b200_reconstruct", "cafe_b200_build_matrices", "cafe_b200_matrix_size",
     "cafe_b200_prune_roots", "cafe_b200_launch_count", "cafe_b200_last_timings", "cafe_b200_root_max", "cafe_b200_pvalues",
     "cafe_b200_branch_probabilities", "cafe_b200_create_multi", "cafe_b200_n_devices", "cafe_b200_alloc_pinned", "cafe_b200_free_pinned",
-    "cafe_b200_set_families_ex", "cafe_b200_plan_program", "cafe_b200_describe", "cafe_b200_fetch_category_likelihoods", "cafe_b200_timing_history", "cafe_b200_host_seconds",
+    "cafe_b200_set_families_ex", "cafe_b200_plan_program", "cafe_b200_describe", "cafe_b200_fetch_category_likelihoods", "cafe_b200_timing_history", "cafe_b200_host_seconds", "cafe_b200_set_build_partition",
 ]
 
 _dp = C.POINTER(C.c_double)
@@ -41,6 +41,10 @@ _i64p = C.POINTER(C.c_int64)
 
 class CafeB200Error(RuntimeError):
     pass
+
+
+#: int gather(void* user, void* mp, size_t mp_slab_bytes, void* mt, size_t mt_slab_bytes, int n_parts, void* cuda_stream)
+GATHER_FN = C.CFUNCTYPE(C.c_int, C.c_void_p, C.c_void_p, C.c_size_t, C.c_void_p, C.c_size_t, C.c_int, C.c_void_p)
 
 
 class _Tree(C.Structure):
@@ -87,6 +91,8 @@ def load_library():
     L.cafe_b200_timing_history.argtypes = [C.c_void_p, C.c_int, _dp]
     L.cafe_b200_host_seconds.restype = C.c_int
     L.cafe_b200_host_seconds.argtypes = [C.c_void_p, _dp]
+    L.cafe_b200_set_build_partition.restype = C.c_int
+    L.cafe_b200_set_build_partition.argtypes = [C.c_void_p, C.c_int, C.c_int, GATHER_FN, C.c_void_p]
     L.cafe_b200_describe.restype = C.c_int
     L.cafe_b200_describe.argtypes = [C.c_void_p, C.c_char_p, C.c_int]
     L.cafe_b200_destroy.argtypes = [C.c_void_p]
@@ -236,6 +242,24 @@ class Engine:
     def set_max_slots(self, n: int):
         """Cap the on-chip vector storage (>= 2): fewer slots force both tree-walking kernels to spill (tests)."""
         self._check(self._lib.cafe_b200_set_option(self._h, OPT_MAX_SLOTS, int(n)), "set_option")
+
+    def set_build_partition(self, part: int, n_parts: int, gather=None):
+        """Distributed matrix build across processes: this context builds slab ``part`` of ``n_parts`` and calls
+        ``gather(mp_ptr, mp_slab_bytes, mt_ptr, mt_slab_bytes, n_parts, cuda_stream_ptr)`` to all-gather the slabs in place
+        (see cafexp_b200.sharded.nccl_matrix_gather).  ``n_parts = 1`` restores the replicated build."""
+        if gather is None:
+            self._gather_cb = GATHER_FN()
+        else:
+            def trampoline(_user, mp, mp_bytes, mt, mt_bytes, parts, stream):
+                try:
+                    gather(mp, mp_bytes, mt, mt_bytes, parts, stream or 0)
+                    return 0
+                except Exception as e:      # noqa: BLE001 — must not propagate through the C frame
+                    import sys
+                    sys.stderr.write(f"cafexp_b200: matrix all-gather failed: {e!r}\n")
+                    return 1
+            self._gather_cb = GATHER_FN(trampoline)          # kept alive as long as the context may call it
+        self._check(self._lib.cafe_b200_set_build_partition(self._h, int(part), int(n_parts), self._gather_cb, None), "set_build_partition")
 
     def set_stream(self, cuda_stream_ptr: int):
         self._check(self._lib.cafe_b200_set_stream(self._h, C.c_void_p(cuda_stream_ptr)), "set_stream")

@@ -37,10 +37,13 @@ def _worker(rank, world, port, q):
         with engine.Engine(tree, counts.astype(np.uint8), MF, MRF, device=rank) as eng:
             job = sharded.ShardedLikelihood(sharded.engine_local_eval(eng), result)
             scores = []
-            for stream in (torch.cuda.current_stream(), torch.cuda.Stream()):           # default stream, then a side stream
-                with torch.cuda.stream(stream):
-                    for _ in range(3):
-                        scores.append(job.score(lams, prior, freq, engine.GAMMA_LINSUM))
+            for distributed_build in (False, True):
+                # replicated matrix build, then: each rank builds half of the matrices, one NCCL all-gather hands them over
+                eng.set_build_partition(rank, world, sharded.nccl_matrix_gather()) if distributed_build else eng.set_build_partition(0, 1)
+                for stream in (torch.cuda.current_stream(), torch.cuda.Stream()):       # default stream, then a side stream
+                    with torch.cuda.stream(stream):
+                        for _ in range(3):
+                            scores.append(job.score(lams, prior, freq, engine.GAMMA_LINSUM))
         q.put((rank, scores))
     finally:
         dist.destroy_process_group()
