@@ -266,6 +266,7 @@ def harness_fit(cuda, devices, timeout, **kw):
         argv += ["--" + key, repr(val) if isinstance(val, float) else str(val)]
     env = dict(os.environ)
     env["CAFE_B200_DEVICES"] = ",".join(str(d) for d in devices)
+    env["OMP_NUM_THREADS"] = str(os.cpu_count() or 1)        # torchrun pins its ranks to one OpenMP thread; this process has the host to itself
     env.pop("CAFE_B200_GEOM", None)
     t0 = time.perf_counter()
     try:

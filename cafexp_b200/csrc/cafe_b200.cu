@@ -28,6 +28,9 @@
 #include <utility>
 #include <vector>
 
+#include <omp.h>
+#include <thread>
+
 #include <nvtx3/nvToolsExt.h>
 
 #include "bd_matrix.cuh"
@@ -101,8 +104,11 @@ struct Shard {
     int* d_parent = nullptr;
     int* d_internal = nullptr;          // [n_nodes] position among internal nodes, -1 for leaves
     unsigned char* d_param = nullptr;   // the parameter block (ParamLayout)
-    double* d_mp = nullptr;
-    double* d_mt = nullptr;
+    // The transition matrices: one block of kstride doubles per unique key = [panelised layout | transposed layout], so that
+    // a builder's slab of keys is ONE contiguous range (one peer copy / one all-gather when the build is distributed).
+    double* d_mat = nullptr;
+    double* d_mp = nullptr;             // = d_mat               (panelised layout of key 0)
+    double* d_mt = nullptr;             // = d_mat + mp_len      (transposed layout of key 0)
     double* d_lgamma = nullptr;
     double* d_err = nullptr;
     size_t err_cap = 0;
@@ -159,7 +165,8 @@ struct cafe_b200_ctx {
     int tmem_entries = 0, n_gspill = 0, tmem_cols = 0, prune_smem = 0;
     int rescale = 0;
     int cap_k = 0;                      // categories the k-dependent buffers are sized for
-    size_t mp_stride = 0, mt_stride = 0;
+    size_t mp_len = 0, mt_len = 0;      // doubles of one key's panelised / transposed layout
+    size_t mp_stride = 0, mt_stride = 0;// doubles between consecutive keys in either layout (both = mp_len + mt_len)
     ParamLayout lay;
     // pinned host image of the parameter block and the error model
     unsigned char* h_param = nullptr;
@@ -344,8 +351,8 @@ ParamLayout make_layout(const cafe_b200_ctx* c, int k)
 
 void free_category_buffers(Shard* s)
 {
-    cudaFree(s->d_param); cudaFree(s->d_mp); cudaFree(s->d_mt); cudaFree(s->d_cat_lk); cudaFree(s->d_fail);
-    s->d_param = nullptr; s->d_mp = s->d_mt = nullptr; s->d_cat_lk = nullptr; s->d_fail = nullptr;
+    cudaFree(s->d_param); cudaFree(s->d_mat); cudaFree(s->d_cat_lk); cudaFree(s->d_fail);
+    s->d_param = nullptr; s->d_mat = s->d_mp = s->d_mt = nullptr; s->d_cat_lk = nullptr; s->d_fail = nullptr;
 }
 
 int ensure_category_buffers(cafe_b200_ctx* c, int k)
@@ -360,8 +367,9 @@ int ensure_category_buffers(cafe_b200_ctx* c, int k)
         CUDA_TRY(c, cudaStreamSynchronize(s->stream));
         free_category_buffers(s);
         CUDA_TRY(c, dev_alloc(&s->d_param, c->lay.total));
-        CUDA_TRY(c, dev_alloc(&s->d_mp, keys * c->mp_stride, true));
-        CUDA_TRY(c, dev_alloc(&s->d_mt, keys * c->mt_stride, true));
+        CUDA_TRY(c, dev_alloc(&s->d_mat, keys * c->mp_stride, true));
+        s->d_mp = s->d_mat;
+        s->d_mt = s->d_mat + c->mp_len;
         CUDA_TRY(c, dev_alloc(&s->d_cat_lk, (size_t)s->n_families * k));
         CUDA_TRY(c, dev_alloc(&s->d_fail, (size_t)s->n_families * k, true));
     }
@@ -439,14 +447,7 @@ int stage_host(cafe_b200_ctx* c, const double* lambdas, int n_lambdas, int k, co
             h_mat_of[cat * t.n_nodes + v] = it->second;
         }
     }
-    // pow(coeff, j) rows from the host libm (src/probability.cpp:125): n_keys * N calls, threaded when there are many
     const int n = c->n;
-    #pragma omp parallel for schedule(static) if ((size_t)n_keys * n > 4000) num_threads(8)
-    for (int key = 0; key < n_keys; ++key) {
-        const double coeff = h_keys[key].coeff;
-        double* pw = h_powc + (size_t)key * n;
-        for (int j = 0; j < n; ++j) pw[j] = std::pow(coeff, (double)j);
-    }
     for (int j = 0; j < c->n; ++j) {
         const double pj = (prior && j < n_prior) ? prior[j] : 0.0;
         h_prior[j] = pj;
@@ -483,6 +484,21 @@ int stage_host(cafe_b200_ctx* c, const double* lambdas, int n_lambdas, int k, co
             h_keys[key] = kp;
             std::fill(h_powc + (size_t)key * n, h_powc + (size_t)(key + 1) * n, 0.0);
         }
+    }
+    // pow(coeff, j) rows from the host libm (src/probability.cpp:125): N calls per key, threaded when there are many.  A
+    // context that builds only one slab of the matrices (distributed build across processes) needs only that slab's rows.
+    int pow_first = 0, pow_last = n_keys;
+    if (c->ext_parts > 1 && builders > 1) {
+        const int per = padded / builders;
+        pow_first = std::min(n_keys, c->ext_part * per);
+        pow_last = std::min(n_keys, (c->ext_part + 1) * per);
+    }
+    const int pow_threads = std::max(1, std::min(8, omp_get_max_threads()));         // honours OMP_NUM_THREADS (torchrun sets 1 per rank)
+    #pragma omp parallel for schedule(static) if ((size_t)(pow_last - pow_first) * n > 4000) num_threads(pow_threads)
+    for (int key = pow_first; key < pow_last; ++key) {
+        const double coeff = h_keys[key].coeff;
+        double* pw = h_powc + (size_t)key * n;
+        for (int j = 0; j < n; ++j) pw[j] = std::pow(coeff, (double)j);
     }
     c->n_keys = n_keys;
     c->n_keys_padded = padded;
@@ -522,19 +538,17 @@ int shard_build(cafe_b200_ctx* c, Shard* s)
     CUDA_TRY(c, cudaGetLastError());
     c->launches++;
     if (builders > 1) {
-        const size_t mp_off = (size_t)key_first * c->mp_stride, mp_cnt = (size_t)per * c->mp_stride;
-        const size_t mt_off = (size_t)key_first * c->mt_stride, mt_cnt = (size_t)per * c->mt_stride;
+        const size_t off = (size_t)key_first * c->mp_stride, cnt = (size_t)per * c->mp_stride;       // both layouts of the slab's keys
         if (c->ext_parts > 1) {
             // across processes: the caller's all-gather (NCCL on this stream) delivers every builder's slab everywhere
-            const int rc = c->gather_cb(c->gather_user, s->d_mp, mp_cnt * sizeof(double), s->d_mt, mt_cnt * sizeof(double), builders, (void*)st);
+            const int rc = c->gather_cb(c->gather_user, s->d_mat, cnt * sizeof(double), builders, (void*)st);
             if (rc != 0) return fail(c, CAFE_B200_ERR_CUDA, "the matrix all-gather callback failed");
         }
         else {
             // inside one context: push this shard's slab to every peer over NVLink (copy engines, stream-ordered after the build)
             for (Shard* d : c->shards) {
                 if (d == s) continue;
-                CUDA_TRY(c, cudaMemcpyPeerAsync(d->d_mp + mp_off, d->device, s->d_mp + mp_off, s->device, mp_cnt * sizeof(double), st));
-                CUDA_TRY(c, cudaMemcpyPeerAsync(d->d_mt + mt_off, d->device, s->d_mt + mt_off, s->device, mt_cnt * sizeof(double), st));
+                CUDA_TRY(c, cudaMemcpyPeerAsync(d->d_mat + off, d->device, s->d_mat + off, s->device, cnt * sizeof(double), st));
             }
             CUDA_TRY(c, cudaEventRecord(s->built, st));
         }
@@ -592,6 +606,13 @@ int launch_prune(cafe_b200_ctx* c, Shard* s, int k, int mode, double* root_out)
     p.cat_lk = s->d_cat_lk; p.fail = s->d_fail; p.root_out = root_out;
     const int64_t items = p.n_tiles * p.n_categories;        // one item = one tile of NG x 16 families of one category
     const int grid = (int)std::min<int64_t>(items, s->sm_count);
+    // the last, partial round of the grid is split into single-group units when that shortens it (prune.cuh)
+    const int64_t leftover = items % grid;
+    p.n_full_items = items; p.n_tail_units = 0;
+    if (c->geom.ng > 1 && items > grid && leftover > 0 && (leftover * c->geom.ng + grid - 1) / grid <= 2 && !getenv("CAFE_B200_NO_TAIL_SPLIT")) {
+        p.n_full_items = items - leftover;
+        p.n_tail_units = leftover * c->geom.ng;
+    }
     CUDA_TRY(c, prune_dispatch(c, p, grid, s->stream, false));
     c->launches++;
     return CAFE_B200_OK;
@@ -872,6 +893,13 @@ int cafe_b200_create_multi(cafe_b200_ctx** out, const cafe_b200_tree* tree, cons
         }                                                                                     \
     } while (0)
 
+    if (n_devices > 1) {
+        // primary contexts are created concurrently (0.3 s each when done one after the other)
+        std::vector<std::thread> warm;
+        for (int i = 0; i < n_devices; ++i) warm.emplace_back([dev = devices[i]] { if (cudaSetDevice(dev) == cudaSuccess) cudaFree(nullptr); });
+        for (std::thread& t : warm) t.join();
+        cudaGetLastError();
+    }
     int smem_limit = INT_MAX;
     for (int i = 0; i < n_devices; ++i) {
         Shard* s = new Shard();
@@ -899,8 +927,9 @@ int cafe_b200_create_multi(cafe_b200_ctx** out, const cafe_b200_tree* tree, cons
     c->mb = c->nr / 32;
     c->kpanels = ((c->mf + 1 + 3) / 4 + PPS - 1) / PPS * PPS;
     c->n_kchunks = c->kpanels / PPS;
-    c->mp_stride = (size_t)c->kpanels * c->nr * 4;
-    c->mt_stride = (size_t)c->kpanels * 4 * c->nr;      // columns padded to whole ring stages (zeros)
+    c->mp_len = (size_t)c->kpanels * c->nr * 4;
+    c->mt_len = (size_t)c->kpanels * 4 * c->nr;         // columns padded to whole ring stages (zeros)
+    c->mp_stride = c->mt_stride = c->mp_len + c->mt_len;
     plan_pupko(c, smem_limit);
 
     if (c->shards.size() > 1) {
@@ -1172,7 +1201,7 @@ int cafe_b200_build_matrices(cafe_b200_ctx* c, const double* lambdas, int n_lamb
     const HostTree& t = c->tree;
     Shard* s = c->shards[0];
     CUDA_TRY(c, cudaSetDevice(s->device));
-    std::vector<double> mt(c->mt_stride);
+    std::vector<double> mt(c->mt_len);
     rc = sync_all(c);
     if (rc) return rc;
     const int* mat_of = reinterpret_cast<const int*>(c->h_param + c->lay.mat_of);
@@ -1181,7 +1210,7 @@ int cafe_b200_build_matrices(cafe_b200_ctx* c, const double* lambdas, int n_lamb
         for (int v = 0; v < t.n_nodes; ++v) {
             double* dst = out + ((size_t)cat * t.n_nodes + v) * c->n * cols;
             if (t.parent[v] < 0) { std::fill(dst, dst + (size_t)c->n * cols, 0.0); continue; }
-            CUDA_TRY(c, cudaMemcpy(mt.data(), s->d_mt + (size_t)mat_of[cat * t.n_nodes + v] * c->mt_stride, c->mt_stride * sizeof(double), cudaMemcpyDeviceToHost));
+            CUDA_TRY(c, cudaMemcpy(mt.data(), s->d_mt + (size_t)mat_of[cat * t.n_nodes + v] * c->mt_stride, c->mt_len * sizeof(double), cudaMemcpyDeviceToHost));
             for (int sz = 0; sz < c->n; ++sz)
                 for (int cc = 0; cc < cols; ++cc) dst[(size_t)sz * cols + cc] = mt[(size_t)cc * c->nr + sz];
         }

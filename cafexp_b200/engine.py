@@ -43,8 +43,8 @@ class CafeB200Error(RuntimeError):
     pass
 
 
-#: int gather(void* user, void* mp, size_t mp_slab_bytes, void* mt, size_t mt_slab_bytes, int n_parts, void* cuda_stream)
-GATHER_FN = C.CFUNCTYPE(C.c_int, C.c_void_p, C.c_void_p, C.c_size_t, C.c_void_p, C.c_size_t, C.c_int, C.c_void_p)
+#: int gather(void* user, void* matrices, size_t slab_bytes, int n_parts, void* cuda_stream)
+GATHER_FN = C.CFUNCTYPE(C.c_int, C.c_void_p, C.c_void_p, C.c_size_t, C.c_int, C.c_void_p)
 
 
 class _Tree(C.Structure):
@@ -245,14 +245,14 @@ class Engine:
 
     def set_build_partition(self, part: int, n_parts: int, gather=None):
         """Distributed matrix build across processes: this context builds slab ``part`` of ``n_parts`` and calls
-        ``gather(mp_ptr, mp_slab_bytes, mt_ptr, mt_slab_bytes, n_parts, cuda_stream_ptr)`` to all-gather the slabs in place
+        ``gather(matrices_ptr, slab_bytes, n_parts, cuda_stream_ptr)`` to all-gather the slabs in place
         (see cafexp_b200.sharded.nccl_matrix_gather).  ``n_parts = 1`` restores the replicated build."""
         if gather is None:
             self._gather_cb = GATHER_FN()
         else:
-            def trampoline(_user, mp, mp_bytes, mt, mt_bytes, parts, stream):
+            def trampoline(_user, matrices, slab_bytes, parts, stream):
                 try:
-                    gather(mp, mp_bytes, mt, mt_bytes, parts, stream or 0)
+                    gather(matrices, slab_bytes, parts, stream or 0)
                     return 0
                 except Exception as e:      # noqa: BLE001 — must not propagate through the C frame
                     import sys

@@ -92,25 +92,24 @@ class _DevicePointer:
 
 def nccl_matrix_gather(group=None) -> Callable:
     """The exchange step of the distributed matrix build (cafe_b200_set_build_partition): every rank has built one slab
-    of the evaluation's transition matrices into its own buffers; one in-place NCCL all-gather per layout over NVLink /
-    NVSwitch hands every slab to every rank (config 5, 8 ranks: 2 x 16 MB sent per rank instead of 2.4 ms of redundant
-    FP64 work on every GPU).  Runs on torch's current stream, which is the stream the engine is bound to."""
+    of the evaluation's transition matrices into its own buffer; ONE in-place NCCL all-gather over NVLink / NVSwitch hands
+    every slab to every rank (config 5, 8 ranks: 32 MB sent per rank instead of 2.4 ms of redundant FP64 work on every
+    GPU).  Runs on torch's current stream, which is the stream the engine is bound to."""
     import torch
     import torch.distributed as dist
     views = {}
 
-    def gather(mp, mp_slab_bytes, mt, mt_slab_bytes, n_parts, stream):
+    def gather(matrices, slab_bytes, n_parts, stream):
         if torch.cuda.current_stream().cuda_stream != stream:
             raise RuntimeError("the engine is not bound to torch's current stream")
         rank = dist.get_rank(group)
         if dist.get_world_size(group) != n_parts:
             raise RuntimeError("build partition and process group disagree")
-        for ptr, slab in ((mp, mp_slab_bytes), (mt, mt_slab_bytes)):
-            key = (ptr, slab, n_parts)
-            if key not in views:
-                views[key] = torch.as_tensor(_DevicePointer(ptr, slab * n_parts), device=torch.device("cuda", torch.cuda.current_device()))
-            full = views[key]
-            dist.all_gather_into_tensor(full, full[rank * slab:(rank + 1) * slab], group=group)
+        key = (matrices, slab_bytes, n_parts)
+        if key not in views:
+            views[key] = torch.as_tensor(_DevicePointer(matrices, slab_bytes * n_parts), device=torch.device("cuda", torch.cuda.current_device()))
+        full = views[key]
+        dist.all_gather_into_tensor(full, full[rank * slab_bytes:(rank + 1) * slab_bytes], group=group)
 
     return gather
 

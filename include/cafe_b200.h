@@ -133,11 +133,11 @@ int  cafe_b200_set_option(cafe_b200_ctx* ctx, int option, int value);
 /* Distributed matrix build across PROCESSES (one single-device context per process / rank).  By
  * default every context builds every transition matrix of an evaluation itself; with a partition announced here it
  * builds only slab `part` of `n_parts` (keys are padded to a whole number per part) and then calls `gather`, which must
- * all-gather the slabs in place on the given stream — mp / mt are this context's matrix buffers, slab i lives at byte
- * offset i * slab_bytes, this rank's own slab is already in place (e.g. ncclAllGather / torch all_gather_into_tensor with
- * sendbuff = recvbuff + part * slab_bytes).  Every rank must evaluate with identical parameters.  Returns 0 on success.
- * (A multi-device context does the same by itself with peer copies over NVLink.) */
-typedef int (*cafe_b200_gather_fn)(void* user, void* mp, size_t mp_slab_bytes, void* mt, size_t mt_slab_bytes, int n_parts, void* cuda_stream);
+ * all-gather the slabs in place on the given stream — `matrices` is this context's matrix buffer (device memory), slab i
+ * lives at byte offset i * slab_bytes, this rank's own slab is already in place (e.g. ncclAllGather / torch
+ * all_gather_into_tensor with sendbuff = recvbuff + part * slab_bytes).  Every rank must evaluate with identical
+ * parameters.  Returns 0 on success.  (A multi-device context does the same by itself with peer copies over NVLink.) */
+typedef int (*cafe_b200_gather_fn)(void* user, void* matrices, size_t slab_bytes, int n_parts, void* cuda_stream);
 int  cafe_b200_set_build_partition(cafe_b200_ctx* ctx, int part, int n_parts, cafe_b200_gather_fn gather, void* user);
 
 /* Enqueue on an existing CUDA stream (cudaStream_t passed as void*; NULL = the legacy default stream)
