@@ -606,13 +606,6 @@ int launch_prune(cafe_b200_ctx* c, Shard* s, int k, int mode, double* root_out)
     p.cat_lk = s->d_cat_lk; p.fail = s->d_fail; p.root_out = root_out;
     const int64_t items = p.n_tiles * p.n_categories;        // one item = one tile of NG x 16 families of one category
     const int grid = (int)std::min<int64_t>(items, s->sm_count);
-    // the last, partial round of the grid is split into single-group units when that shortens it (prune.cuh)
-    const int64_t leftover = items % grid;
-    p.n_full_items = items; p.n_tail_units = 0;
-    if (c->geom.ng > 1 && items > grid && leftover > 0 && (leftover * c->geom.ng + grid - 1) / grid <= 2 && !getenv("CAFE_B200_NO_TAIL_SPLIT")) {
-        p.n_full_items = items - leftover;
-        p.n_tail_units = leftover * c->geom.ng;
-    }
     CUDA_TRY(c, prune_dispatch(c, p, grid, s->stream, false));
     c->launches++;
     return CAFE_B200_OK;

@@ -94,8 +94,6 @@ struct PruneParams {
     int tmem_entries;       // ... and the rest in tensor memory (entries per warp)
     int tmem_cols;          // tensor-memory columns to allocate (power of two >= 32, 0 = none)
     int64_t n_tiles;        // tiles of (groups x 16) families = work items per category
-    int64_t n_full_items;   // items run by all groups (whole rounds of the grid)
-    int64_t n_tail_units;   // single-group units the last partial round is split into (0: no split)
     // device pointers
     const POp* ops;                 // [k][n_ops]
     const LeafRef* leaves;          // [k][n_leafrefs]

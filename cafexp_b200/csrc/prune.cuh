@@ -208,11 +208,7 @@ __global__ void __launch_bounds__(pg_threads(NG, GW, PW), 1) prune_kernel(const 
     __syncthreads();
     asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
 
-    // Work units: the items (tile of NG x 16 families, category) that fill whole rounds of the grid run with all groups;
-    // the items of the last, partial round are split into NG units of ONE group each and dealt out again, so that the
-    // tail costs a fraction of an item instead of a whole one (71 vs 70.4 rounds at 125 000 families per GPU: 0.9 %).
-    // In a tail unit group 0 prunes the unit's 16 families; the other groups only hand the ring stages through.
-    const int64_t n_work = p.n_full_items + p.n_tail_units;
+    const int64_t n_items = p.n_tiles * p.n_categories;
 
     if (warp >= CONSUMERS) {
         // ===== producer warpgroup: give registers back, then PW of its warps stream the matrix K-chunks of every GEMM op
@@ -221,8 +217,7 @@ __global__ void __launch_bounds__(pg_threads(NG, GW, PW), 1) prune_kernel(const 
         const int which = warp - CONSUMERS;
         if (which < PW && lane == 0) {
             uint32_t stage = 0, phase = 0, turn = 0;
-            for (int64_t w = blockIdx.x; w < n_work; w += gridDim.x) {
-                const int64_t item = w < p.n_full_items ? w : p.n_full_items + (w - p.n_full_items) / NG;
+            for (int64_t item = blockIdx.x; item < n_items; item += gridDim.x) {
                 const int cat = (int)(item / p.n_tiles);
                 const POp* ops = p.ops + (size_t)cat * p.n_ops;
                 for (int o = 0; o < p.n_ops; ++o) {
@@ -270,14 +265,10 @@ __global__ void __launch_bounds__(pg_threads(NG, GW, PW), 1) prune_kernel(const 
     int cur = 0;                                  // which of the two buffers holds the current complete vector
     int loaded_cat = -1;                          // category whose program sits in shared memory
 
-    for (int64_t w = blockIdx.x; w < n_work; w += gridDim.x) {
-        const bool tail = w >= p.n_full_items;
-        const int64_t item = tail ? p.n_full_items + (w - p.n_full_items) / NG : w;
+    for (int64_t item = blockIdx.x; item < n_items; item += gridDim.x) {
         const int cat = (int)(item / p.n_tiles);
         const int64_t tile = item - (int64_t)cat * p.n_tiles;
-        // first family of this group (the count matrix is padded to whole tiles); in a tail unit group 0 takes sub-tile w % NG
-        const int64_t fam0 = tile * PFT + (tail ? (int)((w - p.n_full_items) % NG) * GFT : fbase);
-        const bool ghost = tail && group != 0;
+        const int64_t fam0 = tile * PFT + fbase;  // first family of this group (the count matrix is padded to whole tiles)
         // this group's 16 count rows: the staged tile, or straight from the (padded) global matrix
         const unsigned char* cnt = p.counts_in_smem ? cnt_s + (size_t)fbase * p.n_leaves * p.cnt_width
                                                     : reinterpret_cast<const unsigned char*>(p.counts) + fam0 * p.n_leaves * p.cnt_width;
@@ -293,20 +284,6 @@ __global__ void __launch_bounds__(pg_threads(NG, GW, PW), 1) prune_kernel(const 
             for (int i = tid; i < n16; i += CONSUMERS * 32) dst[i] = i < n16_ops ? __ldg(src_ops + i) : __ldg(src_leaf + (i - n16_ops));
             asm volatile("bar.sync 14, %0;" ::"n"(CONSUMERS * 32) : "memory");
             loaded_cat = cat;
-        }
-        if (ghost) {
-            // keep the shared matrix stream moving: every stage of every GEMM op is waited for and released, nothing is read
-            const POp* gops = p.ops_in_smem ? ops_s : p.ops + (size_t)cat * p.n_ops;
-            for (int o = 0; o < p.n_ops; ++o) {
-                if (gops[o].type != POP_GEMM) continue;
-                for (int left = p.n_kchunks; left > 0; left -= CPS) {
-                    mbar_wait_u32(full_u + stage * 8u, phase);
-                    __syncwarp();
-                    if (lane == 0) mbar_arrive_u32(empty_u + stage * 8u);
-                    if (++stage == (uint32_t)p.n_stages) { stage = 0; phase ^= 1; }
-                }
-            }
-            continue;
         }
         group_sync(group, GROUP_THREADS);         // previous item fully finished with this group's shared memory
         if (p.counts_in_smem) {

@@ -1,5 +1,5 @@
 """Randomised differential test of the CUDA path against the CPU oracle: random tree shapes (binary and n-ary,
-balanced and caterpillar), matrix sizes across every row-block count (N = 6 .. 250), rate categories, multiple
+balanced and caterpillar), matrix sizes across every row-block count (N = 6 .. 250, and 261 .. 512 for the likelihood), rate categories, multiple
 lambdas, error models with 3 and 5 deviations, shared-memory slot limits that force spills, ragged family counts,
 power-of-two rescaling.  Every case checks evaluation, root vectors, the p-value statistic and the Pupko
 reconstruction.  Needs a B200."""
@@ -82,6 +82,42 @@ def test_random_big_tree_against_oracle(seed):
     check_case(make_case(seed, big=True))
 
 
+def make_large_matrix_case(seed):
+    """Matrix sizes 257 .. 512 (round 1 stopped at 256): the likelihood runs with eight warps per group and 64-row
+    blocks, leaf counts above 255 travel and live on the device as uint16, lgamma arguments pass the reference's
+    1024-entry table (src/probability.cpp:58-64: libm beyond it)."""
+    rng = np.random.default_rng(seed)
+    n_leaves = int(rng.choice([3, 4, 6]))
+    flat = hostio.flatten_tree(hostio.parse_newick(random_newick(rng, n_leaves, str(rng.choice(["random", "caterpillar"])), int(rng.choice([2, 2, 3])))))
+    mf = int(rng.choice([260, 299, 319, 320, 383, 400, 447, 480, 511]))
+    mrf = int(np.clip(mf + rng.integers(-mf // 2, 1), 1, 511))
+    n_lambdas = int(rng.choice([1, 2]))
+    flat.lambda_index[:] = rng.integers(0, n_lambdas, size=flat.n_nodes)
+    F = int(rng.choice([3, 17, 33]))
+    ndev = int(rng.choice([0, 0, 3]))
+    hi = mf - 2
+    counts = np.minimum(rng.poisson(rng.uniform(5.0, 120.0), size=(F, flat.n_leaves)), hi).astype(np.int32)
+    counts[rng.integers(0, F), rng.integers(0, flat.n_leaves)] = hi            # a count above 255: two bytes per count
+    k = int(rng.choice([1, 2, 3]))
+    lam = rng.uniform(0.0005, 0.01, size=n_lambdas)
+    freq, rate = orc.get_gamma(k, float(rng.uniform(0.3, 2.0))) if k > 1 else (np.ones(1), np.ones(1))
+    err = None
+    if ndev:
+        err = rng.uniform(0.0, 1.0, size=(int(counts.max()) + 1, ndev))
+        err /= err.sum(axis=1, keepdims=True)
+        err[0, : (ndev - 1) // 2] = 0.0
+    return dict(flat=flat, mf=mf, mrf=mrf, counts=counts, k=k, lams=rate[:, None] * lam[None, :], freq=freq, err=err, slots=int(rng.choice([0, 2])),
+                rescale=bool(rng.random() < 0.3), n_leaves=n_leaves, shape="large-matrix")
+
+
+@pytest.mark.parametrize("seed", range(2000, 2006))
+def test_matrix_sizes_above_256_against_oracle(seed):
+    c = make_large_matrix_case(seed)
+    check_case(c)
+    with engine.Engine(c["flat"], c["counts"], c["mf"], c["mrf"]) as eng:
+        assert "gw=8" in eng.describe() and "count_bytes=2" in eng.describe()
+
+
 @pytest.mark.parametrize("seed", range(int(os.environ.get("CAFE_B200_FUZZ_SEEDS", "40"))))
 def test_random_case_against_oracle(seed):
     check_case(make_case(seed))
@@ -113,9 +149,15 @@ def check_case(c):
         if c["err"] is None:
             # root vectors of the first category, and the p-value statistic under the first lambda set
             roots = eng.prune_roots(lams[:1])[:, 0, :]
-            ref = np.stack([orc.inference_prune(flat, counts[i], lams[0], mf, mrf) for i in range(min(len(counts), 12))])
+            n_ref = 12 if max(mf, mrf) < 256 else 2        # the oracle rebuilds every matrix per call: O(N^3) each above 256
+            ref = np.stack([orc.inference_prune(flat, counts[i], lams[0], mf, mrf) for i in range(min(len(counts), n_ref))])
             assert np.allclose(roots[: len(ref)], ref, rtol=RTOL, atol=1e-300)
             assert np.allclose(eng.root_max(lams[0]), orc.root_max(flat, counts, lams[0], mf, mrf), rtol=RTOL, atol=1e-300)
             # Pupko reconstruction (ignores the error model in the reference too): exact
             prior_sz = orc.prior_uniform(mrf, None, min(mf, mrf) + 1)
-            assert np.array_equal(eng.reconstruct(lams, prior_sz), orc.reconstruct(flat, counts, lams, prior_sz, mf, mrf)), c
+            if max(mf, mrf) + 1 <= 256:
+                assert np.array_equal(eng.reconstruct(lams, prior_sz), orc.reconstruct(flat, counts, lams, prior_sz, mf, mrf)), c
+            else:
+                # the reconstruction kernel keeps 32-family tiles and one-byte argmax tables: matrix sizes up to 256
+                with pytest.raises(engine.CafeB200Error, match="ERR_LIMIT"):
+                    eng.reconstruct(lams, prior_sz)
