@@ -112,7 +112,8 @@ struct Shard {
     double* d_lgamma = nullptr;
     double* d_err = nullptr;
     size_t err_cap = 0;
-    double* d_cat_lk = nullptr;
+    double* d_cat_km = nullptr;         // [k][F] category likelihoods as the pruning kernel writes them
+    double* d_cat_lk = nullptr;         // [F][k] the same, family-major (finalize_kernel), what callers read
     uint8_t* d_fail = nullptr;
     double* d_family_lnl = nullptr;
     uint8_t* d_family_fail = nullptr;
@@ -351,8 +352,8 @@ ParamLayout make_layout(const cafe_b200_ctx* c, int k)
 
 void free_category_buffers(Shard* s)
 {
-    cudaFree(s->d_param); cudaFree(s->d_mat); cudaFree(s->d_cat_lk); cudaFree(s->d_fail);
-    s->d_param = nullptr; s->d_mat = s->d_mp = s->d_mt = nullptr; s->d_cat_lk = nullptr; s->d_fail = nullptr;
+    cudaFree(s->d_param); cudaFree(s->d_mat); cudaFree(s->d_cat_lk); cudaFree(s->d_cat_km); cudaFree(s->d_fail);
+    s->d_param = nullptr; s->d_mat = s->d_mp = s->d_mt = nullptr; s->d_cat_lk = s->d_cat_km = nullptr; s->d_fail = nullptr;
 }
 
 int ensure_category_buffers(cafe_b200_ctx* c, int k)
@@ -371,6 +372,7 @@ int ensure_category_buffers(cafe_b200_ctx* c, int k)
         s->d_mp = s->d_mat;
         s->d_mt = s->d_mat + c->mp_len;
         CUDA_TRY(c, dev_alloc(&s->d_cat_lk, (size_t)s->n_families * k));
+        CUDA_TRY(c, dev_alloc(&s->d_cat_km, (size_t)s->n_families * k));
         CUDA_TRY(c, dev_alloc(&s->d_fail, (size_t)s->n_families * k, true));
     }
     if (c->lay.total > c->h_param_bytes) {
@@ -603,7 +605,7 @@ int launch_prune(cafe_b200_ctx* c, Shard* s, int k, int mode, double* root_out)
     p.logprior = reinterpret_cast<const double*>(s->d_param + c->lay.logprior);
     p.cat_probs = reinterpret_cast<const double*>(s->d_param + c->lay.catprobs);
     p.scratch = s->d_pscratch;
-    p.cat_lk = s->d_cat_lk; p.fail = s->d_fail; p.root_out = root_out;
+    p.cat_lk = s->d_cat_km; p.fail = s->d_fail; p.root_out = root_out;
     const int64_t items = p.n_tiles * p.n_categories;        // one item = one tile of NG x 16 families of one category
     const int grid = (int)std::min<int64_t>(items, s->sm_count);
     CUDA_TRY(c, prune_dispatch(c, p, grid, s->stream, false));
@@ -749,7 +751,7 @@ int enqueue_eval(cafe_b200_ctx* c, const double* lambdas, int n_lambdas, const d
         cudaStream_t st = s->stream;
         CUDA_TRY(c, cudaEventRecord(s->ev[2], st));
         const int blocks = (int)std::max<int64_t>(1, std::min<int64_t>((s->n_families + RED_THREADS - 1) / RED_THREADS, MAX_PARTIALS));
-        finalize_kernel<<<blocks, RED_THREADS, 0, st>>>(s->n_families, k, mode, s->d_cat_lk, s->d_fail, s->d_family_lnl, s->d_family_fail, s->d_partial);
+        finalize_kernel<<<blocks, RED_THREADS, 0, st>>>(s->n_families, k, mode, s->d_cat_km, s->d_fail, s->d_family_lnl, s->d_family_fail, s->d_partial, s->d_cat_lk);
         CUDA_TRY(c, cudaGetLastError());
         final_sum_kernel<<<1, RED_THREADS, 0, st>>>(blocks, s->d_partial, result_device_single ? result_device_single : s->d_result);
         CUDA_TRY(c, cudaGetLastError());
@@ -1258,7 +1260,7 @@ int cafe_b200_root_max(cafe_b200_ctx* c, const double* lambdas, int n_lambdas, d
         CUDA_TRY(c, cudaEventRecord(s->ev[2], s->stream));
         s->ev_valid[2] = true; s->ev_valid[3] = s->ev_valid[4] = false;
         if (s->n_families)
-            CUDA_TRY(c, cudaMemcpyAsync(out + s->first, s->d_cat_lk, (size_t)s->n_families * sizeof(double), cudaMemcpyDeviceToHost, s->stream));
+            CUDA_TRY(c, cudaMemcpyAsync(out + s->first, s->d_cat_km, (size_t)s->n_families * sizeof(double), cudaMemcpyDeviceToHost, s->stream));
     }
     rc = sync_all(c);
     if (rc) return rc;

@@ -108,8 +108,8 @@ struct PruneParams {
     const double* cat_probs;        // [k]
     double* scratch;                // [grid][n_gspill][4*RB][consumer threads]
     // outputs
-    double* cat_lk;                 // [F][k]   (gamma)  or family lnL [F] (base)
-    uint8_t* fail;                  // [F][k]
+    double* cat_lk;                 // [k][F]   (gamma: category-major, so that a category pass writes whole sectors)  or family lnL [F] (base)
+    uint8_t* fail;                  // [k][F]
     double* root_out;               // [F][k][mrf] or null (inspection)
 };
 

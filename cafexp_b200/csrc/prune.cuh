@@ -584,8 +584,8 @@ __global__ void __launch_bounds__(pg_threads(NG, GW, PW), 1) prune_kernel(const 
                             nonzero |= __shfl_xor_sync(0xffffffffu, nonzero, off);
                         }
                         if (lane == 0) {
-                            p.cat_lk[fam * p.n_categories + cat] = best * p.cat_probs[cat];
-                            p.fail[fam * p.n_categories + cat] = nonzero ? 0 : 1;
+                            p.cat_lk[(size_t)cat * p.n_families + fam] = best * p.cat_probs[cat];
+                            p.fail[(size_t)cat * p.n_families + fam] = nonzero ? 0 : 1;
                         }
                     }
                 }

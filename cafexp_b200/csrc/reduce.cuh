@@ -19,9 +19,12 @@ namespace cafe {
 
 constexpr int RED_THREADS = 256;
 
+// cat_lk / fail arrive category-major [k][F] (what a category pass of the pruning kernel writes contiguously); the
+// family-major [F][k] copy the callers read (gamma_model::_category_likelihoods) is written here.
 __global__ void __launch_bounds__(RED_THREADS) finalize_kernel(int64_t n_families, int k, int mode, const double* __restrict__ cat_lk,
                                                                const uint8_t* __restrict__ fail, double* __restrict__ family_lnl,
-                                                               uint8_t* __restrict__ family_fail, double* __restrict__ partial)
+                                                               uint8_t* __restrict__ family_fail, double* __restrict__ partial,
+                                                               double* __restrict__ cat_lk_fm)
 {
     __shared__ double s_sum[RED_THREADS];
     __shared__ double s_bad[RED_THREADS];
@@ -33,8 +36,10 @@ __global__ void __launch_bounds__(RED_THREADS) finalize_kernel(int64_t n_familie
         else {
             double fam = 0.0;
             for (int c = 0; c < k; ++c) {
-                failed |= fail[i * k + c] != 0;
-                fam += cat_lk[i * k + c];
+                failed |= fail[(size_t)c * n_families + i] != 0;
+                const double v = cat_lk[(size_t)c * n_families + i];
+                fam += v;                                     // ascending category, as std::accumulate (src/gamma_core.cpp:207)
+                cat_lk_fm[i * k + c] = v;
             }
             lnl = log(fam);
         }
