@@ -12,9 +12,6 @@ namespace cafe {
 // V[family][size] with a padded stride so that FP64 MMA B-fragments load without bank conflicts.
 // ---------------------------------------------------------------------------------------------
 constexpr int FT = 32;                  // families per tile (MMA N dimension = 4 n8 blocks)
-constexpr int CONSUMER_WARPS = 8;       // 4 (rows) x 2 (family columns)
-constexpr int CONSUMER_THREADS = CONSUMER_WARPS * 32;
-constexpr int PRUNE_THREADS = CONSUMER_THREADS + 32;   // + 1 producer warp issuing bulk copies
 constexpr int STAGES = 4;               // ring of matrix K-chunks (reconstruction kernel)
 constexpr int MAX_STAGES = 8;           // pruning kernel: 2, 4 or 8 stages chosen at create (power of two)
 constexpr int PPS = 2;                  // K panels (of 4 columns) per stage
@@ -202,11 +199,6 @@ __device__ __forceinline__ void bulk_copy_g2s(void* smem_dst, const void* gmem_s
 __device__ __forceinline__ void dmma_m8n8k4(double& d0, double& d1, double a, double b)
 {
     asm volatile("mma.sync.aligned.m8n8k4.row.col.f64.f64.f64.f64 {%0,%1}, {%2}, {%3}, {%0,%1};" : "+d"(d0), "+d"(d1) : "d"(a), "d"(b));
-}
-
-__device__ __forceinline__ void consumer_sync()
-{
-    asm volatile("bar.sync 1, %0;" ::"n"(CONSUMER_THREADS) : "memory");
 }
 
 }  // namespace cafe

@@ -333,3 +333,102 @@ def test_two_and_three_group_layouts_give_identical_results(mammal, monkeypatch)
     assert np.array_equal(two["cat_lk"], three["cat_lk"], equal_nan=True)
     assert np.array_equal(roots2, roots3)
     assert two["score"] == three["score"] and two["n_failed"] == three["n_failed"]
+
+
+def test_rescale_survives_subnormal_and_zero_intermediates():
+    """Round-1 advisor finding: the renormalisation multiplied by 2^-e, which overflows when the row maximum is
+    subnormal, and scaled dead rows.  A 70-leaf caterpillar with large counts drives the un-rescaled partial likelihoods
+    through the subnormal range to zero (the reference arithmetic gives -inf); with CAFE_B200_OPT_RESCALE the likelihood
+    must come out finite and equal to the same recursion carried out with explicit exponents in numpy."""
+    n_leaves, mf, mrf, lam = 70, 60, 40, 0.0004
+    newick = "L0:3"
+    for i in range(1, n_leaves):
+        newick = f"({newick},L{i}:{3 + i % 5}):2"
+    tree = hostio.flatten_tree(hostio.parse_newick(newick + ";"))
+    rng = np.random.default_rng(11)
+    counts = rng.integers(25, 45, size=(37, tree.n_leaves)).astype(np.int32)
+    prior = orc.prior_uniform(mrf, None, max(mf, mrf) + 1)
+    n = max(mf, mrf) + 1
+    mats = {v: orc.build_matrix(n, lam, tree.branch[v])[:, :mf + 1] for v in range(tree.n_nodes - 1)}
+
+    def scaled_lnl(row):
+        vec, exp = {}, {}
+        for v in range(tree.n_nodes):
+            kids = tree.child_list[tree.child_offset[v]:tree.child_offset[v + 1]]
+            if len(kids) == 0:
+                continue
+            acc, e = np.ones(n), 0
+            for c in kids:
+                if tree.leaf_col[c] >= 0:
+                    f = mats[c][:, row[tree.leaf_col[c]]]
+                else:
+                    f = mats[c] @ vec[c][:mf + 1]
+                    e += exp[c]
+                acc = acc * f
+                if acc.max() > 0:
+                    _, ex = np.frexp(acc.max())
+                    acc, e = np.ldexp(acc, -ex), e + int(ex)     # exact power-of-two renormalisation after every factor
+            vec[v], exp[v] = acc, e
+        root = tree.n_nodes - 1
+        with np.errstate(divide="ignore"):
+            return float(np.max(np.log(vec[root][1:mrf + 1]) + np.log(prior[:mrf])) + exp[root] * np.log(2.0))
+
+    want = np.array([scaled_lnl(r) for r in counts])
+    assert np.isfinite(want).all() and want.min() < -750, "the case must leave the double range without rescaling"
+    with engine.Engine(tree, counts, mf, mrf) as eng:
+        plain = eng.infer([[lam]], prior)
+        assert not np.isfinite(plain["family_lnl"]).all()          # reference arithmetic: underflow to zero, lnL = -inf
+        eng.set_rescale(True)
+        got = eng.infer([[lam]], prior)
+        assert np.isfinite(got["family_lnl"]).all()
+        assert rel_err(got["family_lnl"], want) < 1e-11
+        eng.set_max_slots(2)                                      # parked products in device scratch instead of tensor memory
+        again = eng.infer([[lam]], prior)
+        assert np.array_equal(again["family_lnl"], got["family_lnl"])
+
+
+def test_rescale_with_a_subnormal_row_maximum():
+    """One node whose vector is already subnormal when it completes (a 34-leaf star with alternating counts 10 / 20:
+    no parent size explains both, the largest product is ~1e-315): the renormalisation must scale it by ldexp (2^-e itself would
+    overflow) and the likelihood must stay finite and close to the exactly-scaled recursion (the subnormal entries have
+    lost low bits, so this is not a 1e-11 comparison)."""
+    star = "(" + ",".join(f"S{i}:5" for i in range(34)) + "):3"
+    tree = hostio.flatten_tree(hostio.parse_newick(f"({star},(A:4,B:4):2);"))
+    mf, mrf, lam = 60, 40, 0.0005
+    n = max(mf, mrf) + 1
+    prior = orc.prior_uniform(mrf, None, n)
+    names = tree.leaf_names
+    base = np.array([[(10 if int(nm[1:]) % 2 == 0 else 20) if nm.startswith("S") else 15 for nm in names]], np.int32)
+    counts = np.repeat(base, 20, axis=0)
+    counts[:, [names.index("A"), names.index("B")]] += np.arange(20)[:, None] % 7
+    mats = {v: orc.build_matrix(n, lam, tree.branch[v])[:, :mf + 1] for v in range(tree.n_nodes - 1)}
+    star_node = tree.parent[[v for v in range(tree.n_nodes) if tree.names[v] == "S0"][0]]
+    plain_star = np.ones(n)
+    for c in tree.child_list[tree.child_offset[star_node]:tree.child_offset[star_node + 1]]:
+        plain_star = plain_star * mats[c][:, counts[0, tree.leaf_col[c]]]
+    assert 0 < plain_star.max() < 2.3e-308, f"the star's vector must be subnormal ({plain_star.max()})"
+
+    def scaled_lnl(row):
+        vec, exp = {}, {}
+        for v in range(tree.n_nodes):
+            kids = tree.child_list[tree.child_offset[v]:tree.child_offset[v + 1]]
+            if len(kids) == 0:
+                continue
+            acc, e = np.ones(n), 0
+            for c in kids:
+                f = mats[c][:, row[tree.leaf_col[c]]] if tree.leaf_col[c] >= 0 else mats[c] @ vec[c][:mf + 1]
+                e += 0 if tree.leaf_col[c] >= 0 else exp[c]
+                acc = acc * f
+                _, ex = np.frexp(acc.max())
+                acc, e = np.ldexp(acc, -ex), e + int(ex)
+            vec[v], exp[v] = acc, e
+        root = tree.n_nodes - 1
+        with np.errstate(divide="ignore"):
+            return float(np.max(np.log(vec[root][1:mrf + 1]) + np.log(prior[:mrf])) + exp[root] * np.log(2.0))
+
+    want = np.array([scaled_lnl(r) for r in counts])
+    with engine.Engine(tree, counts, mf, mrf) as eng:
+        eng.set_rescale(True)
+        got = eng.infer([[lam]], prior)["family_lnl"]
+    assert np.isfinite(got).all(), got
+    assert np.max(np.abs(got - want)) < 1e-3 * np.max(np.abs(want)), (got[:4], want[:4])
