@@ -155,7 +155,6 @@ struct cafe_b200_ctx {
     // reconstruction kernel (32-family tiles, slot machine)
     Schedule sched;
     int n_slots = 0, hw_slots = 0;
-    int pupko_warps = 8;                // consumer warps of the reconstruction kernel (CAFE_B200_PUPKO_WARPS: 8 or 16)
     // pruning kernel (stack machine)
     Program prog;
     PruneGeom geom = {0, 4, 2, 2, 2};
@@ -226,19 +225,7 @@ cudaError_t prune_dispatch(const cafe_b200_ctx* c, const PruneParams& p, int gri
 }
 
 template <int MB>
-cudaError_t pupko_attr_mb(int smem)
-{
-    cudaError_t e = cudaFuncSetAttribute(pupko_kernel<MB, 8>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
-    if (e == cudaSuccess) e = cudaFuncSetAttribute(pupko_kernel<MB, 16>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
-    return e;
-}
-
-template <int MB>
-void pupko_launch_mb(int warps, int grid, int smem, cudaStream_t st, const PupkoParams& p)
-{
-    if (warps == 16) pupko_kernel<MB, 16><<<grid, pupko_threads(16), smem, st>>>(p);
-    else pupko_kernel<MB, 8><<<grid, pupko_threads(8), smem, st>>>(p);
-}
+cudaError_t pupko_attr_mb(int smem) { return cudaFuncSetAttribute(pupko_kernel<MB>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem); }
 
 template <int MB>
 int pupko_smem_mb(int slots) { return PupkoSmem<MB>::total_bytes(slots); }
@@ -657,7 +644,7 @@ int launch_pupko(cafe_b200_ctx* c, Shard* s, int k)
     p.mt = s->d_mt; p.mt_stride = c->mt_stride; p.prior = reinterpret_cast<const double*>(s->d_param + c->lay.prior);
     p.scratch = s->d_scratch; p.ctab = s->d_ctab; p.states = s->d_states;
     int smem = 0;
-    MB_SWITCH(c->mb, (smem = PupkoSmem<MB_>::total_bytes(c->n_slots), pupko_launch_mb<MB_>(c->pupko_warps, grid, smem, s->stream, p)));
+    MB_SWITCH(c->mb, (smem = PupkoSmem<MB_>::total_bytes(c->n_slots), pupko_kernel<MB_><<<grid, pupko_threads(PUPKO_WARPS), smem, s->stream>>>(p)));
     CUDA_TRY(c, cudaGetLastError());
     c->launches++;
     return CAFE_B200_OK;
@@ -890,7 +877,6 @@ int cafe_b200_create_multi(cafe_b200_ctx** out, const cafe_b200_tree* tree, cons
     c->cnt_width = c->mf <= 255 ? 1 : 2;
     c->lg_len = 2 * c->n + 2;                    // lgamma arguments reach s + c <= 2 (N - 1)           src/probability.cpp:58-64
     c->prog = ProgramBuilder(t).build();
-    if (const char* e = getenv("CAFE_B200_PUPKO_WARPS")) c->pupko_warps = atoi(e) == 16 ? 16 : 8;
 
 #define CREATE_TRY(call)                                                                      \
     do {                                                                                      \

@@ -65,7 +65,7 @@ struct PupkoSmem {
 };
 
 constexpr int JC = PPS * 4;     // child sizes per ring stage
-constexpr int PUPKO_MAX_WARPS = 16;
+constexpr int PUPKO_WARPS = 8;           // consumer warps
 __host__ __device__ constexpr int pupko_threads(int cw) { return (cw + 1) * 32; }     // + 1 producer warp
 
 // One child size j against four families of one parent-size row: val_f = v_f * m, strict '>' keeps the first maximum
@@ -101,32 +101,17 @@ __device__ __forceinline__ void maxprod4(double& b0, double& b1, double& b2, dou
         : "d"(v0), "d"(v1), "d"(v2), "d"(v3), "d"(m), "r"(j));
 }
 
-// Two families per warp (16 consumer warps per block: four per sub-partition instead of two, half the state per thread).
-__device__ __forceinline__ void maxprod2(double& b0, double& b1, int& a0, int& a1, double v0, double v1, double m, int j)
+// Eight consumer warps (four families each) + one producer warp.  A 16-warp variant (two families per warp, 92 registers,
+// four warps per sub-partition) measured the same 324.0 ms: the bound is not latency but the two half-rate pipes — FP64
+// (multiply, compare) and ALU (two 64-bit selects + one 32-bit select per element) are together busy all the time
+// (ncu: 42 % + 64 %), 10 cycles per element and sub-partition; ptxas turns predicated moves and multiply-add "moves"
+// back into selects, so the selects cannot be moved to the FMA pipe.
+template <int MB>
+__global__ void __launch_bounds__(pupko_threads(PUPKO_WARPS), 1) pupko_kernel(const PupkoParams p)
 {
-    asm("{\n"
-        ".reg .pred p0, p1;\n"
-        ".reg .f64 t0, t1;\n"
-        "mul.rn.f64 t0, %4, %6;\n"
-        "mul.rn.f64 t1, %5, %6;\n"
-        "setp.gt.f64 p0, t0, %0;\n"
-        "setp.gt.f64 p1, t1, %1;\n"
-        "@p0 mov.f64 %0, t0;\n"
-        "@p1 mov.f64 %1, t1;\n"
-        "@p0 mov.s32 %2, %7;\n"
-        "@p1 mov.s32 %3, %7;\n"
-        "}\n"
-        : "+d"(b0), "+d"(b1), "+r"(a0), "+r"(a1)
-        : "d"(v0), "d"(v1), "d"(m), "r"(j));
-}
-
-// CW = consumer warps (8: four families per warp; 16: two).
-template <int MB, int CW>
-__global__ void __launch_bounds__(pupko_threads(CW), 1) pupko_kernel(const PupkoParams p)
-{
-    constexpr int CONSUMER_WARPS = CW;
-    constexpr int CONSUMER_THREADS = CW * 32;
-    auto consumer_sync = [] { asm volatile("bar.sync 1, %0;" ::"n"(CW * 32) : "memory"); };
+    constexpr int CONSUMER_WARPS = PUPKO_WARPS;
+    constexpr int CONSUMER_THREADS = PUPKO_WARPS * 32;
+    auto consumer_sync = [] { asm volatile("bar.sync 1, %0;" ::"n"(PUPKO_WARPS * 32) : "memory"); };
     using L = PupkoSmem<MB>;
     constexpr int NR = L::NR;
     constexpr int LDV = L::LDV;
@@ -246,24 +231,17 @@ __global__ void __launch_bounds__(pupko_threads(CW), 1) pupko_kernel(const Pupko
                     // Columns beyond max_family_size are zero in the transposed matrix (padding up to whole stages), so
                     // their products are 0 (or NaN against a stale slot entry): neither beats a maximum that is >= 0
                     // after j = 0 — no bounds test in the loop.
-                    static_assert(FPW == 4 || FPW == 2, "maxprod4 / maxprod2 handle the families of a warp");
+                    static_assert(FPW == 4, "maxprod4 handles the four families of a warp");
                     #pragma unroll
                     for (int jj = 0; jj < JC; ++jj) {
                         const int j = ch * JC + jj;
                         double m[MB];
                         #pragma unroll
                         for (int i = 0; i < MB; ++i) m[i] = m_stage[jj * NR + 32 * i];
-                        if constexpr (FPW == 4) {
-                            const double v0 = vsrc[0 * LDV + j], v1 = vsrc[1 * LDV + j], v2 = vsrc[2 * LDV + j], v3 = vsrc[3 * LDV + j];
-                            #pragma unroll
-                            for (int i = 0; i < MB; ++i)
-                                maxprod4(best[0][i], best[1][i], best[2][i], best[3][i], arg[0][i], arg[1][i], arg[2][i], arg[3][i], v0, v1, v2, v3, m[i], j);
-                        }
-                        else {
-                            const double v0 = vsrc[0 * LDV + j], v1 = vsrc[1 * LDV + j];
-                            #pragma unroll
-                            for (int i = 0; i < MB; ++i) maxprod2(best[0][i], best[1][i], arg[0][i], arg[1][i], v0, v1, m[i], j);
-                        }
+                        const double v0 = vsrc[0 * LDV + j], v1 = vsrc[1 * LDV + j], v2 = vsrc[2 * LDV + j], v3 = vsrc[3 * LDV + j];
+                        #pragma unroll
+                        for (int i = 0; i < MB; ++i)
+                            maxprod4(best[0][i], best[1][i], best[2][i], best[3][i], arg[0][i], arg[1][i], arg[2][i], arg[3][i], v0, v1, v2, v3, m[i], j);
                     }
                     __syncwarp();
                     if (lane == 0) mbar_arrive(&empty_bar[stage]);
