@@ -265,7 +265,11 @@ def harness_fit(cuda, devices, timeout, **kw):
             continue
         argv += ["--" + key, repr(val) if isinstance(val, float) else str(val)]
     env = dict(os.environ)
-    env["CAFE_B200_DEVICES"] = ",".join(str(d) for d in devices)
+    # The process sees only the devices it uses: cuInit initialises every VISIBLE device (about 0.7 s each on an 8-GPU B200
+    # node — 5.6 s before the first kernel of a 1-device fit otherwise).  Ordinals inside the process are 0 .. n-1.
+    visible = [v.strip() for v in os.environ.get("CUDA_VISIBLE_DEVICES", "").split(",") if v.strip()]
+    env["CUDA_VISIBLE_DEVICES"] = ",".join(visible[d] if d < len(visible) else str(d) for d in devices)
+    env["CAFE_B200_DEVICES"] = ",".join(str(i) for i in range(len(devices)))
     env["OMP_NUM_THREADS"] = str(os.cpu_count() or 1)        # torchrun pins its ranks to one OpenMP thread; this process has the host to itself
     env.pop("CAFE_B200_GEOM", None)
     t0 = time.perf_counter()
