@@ -143,15 +143,16 @@ __device__ __forceinline__ int load_count(const unsigned char* base, int i, int 
     return width == 1 ? (int)base[i] : (int)reinterpret_cast<const uint16_t*>(base)[i];
 }
 
-// Leaf factor of ONE family column of this thread's accumulator fragment (RB values, rows row0 + 8 i): column `obs` of the
+// Leaf factor of ONE family column (RB values, rows row0 + STEP i: STEP = 8 in the accumulator-fragment layout, 32 in the
+// row-major passes): column `obs` of the
 // leaf's transposed matrix, or — with an error model — sum over deviations, ascending child size, no FMA
 // (src/probability.cpp:182-193 feeding src/matrix_cache.cpp:48-54).  mt points at row0 of the leaf's matrix.
-template <int RB, int NR>
+template <int RB, int NR, int STEP = 8>
 __device__ __forceinline__ void leaf_column(double (&v)[RB], const double* mt, int obs, const double* err, int err_ndev, int mf)
 {
     if (err == nullptr) {
         #pragma unroll
-        for (int i = 0; i < RB; ++i) v[i] = __ldg(mt + (size_t)obs * NR + i * 8);
+        for (int i = 0; i < RB; ++i) v[i] = __ldg(mt + (size_t)obs * NR + i * STEP);
     }
     else {
         #pragma unroll
@@ -162,7 +163,7 @@ __device__ __forceinline__ void leaf_column(double (&v)[RB], const double* mt, i
             if (c < 0 || c > mf) continue;
             const double pe = __ldg(err + (size_t)obs * err_ndev + d);
             #pragma unroll
-            for (int i = 0; i < RB; ++i) v[i] = __dadd_rn(v[i], __dmul_rn(__ldg(mt + (size_t)c * NR + i * 8), pe));
+            for (int i = 0; i < RB; ++i) v[i] = __dadd_rn(v[i], __dmul_rn(__ldg(mt + (size_t)c * NR + i * STEP), pe));
         }
     }
 }
@@ -428,21 +429,22 @@ __global__ void __launch_bounds__(pg_threads(NG, GW, PW), 1) prune_kernel(const 
                             }
                     }
                 }
-                if (op.n_post > 0) {
+                // leaves after the internal child: two L1 / L2 round trips per leaf — the loads of two family columns of the
+                // fragment are in flight together (all four would not fit the 160 registers of the three-group geometry)
+                for (int q = 0; q < op.n_post; ++q) {
+                    const LeafRef lr = lrs[op.n_pre + q];
+                    const double* mt = p.mt + (size_t)lr.mat * p.mt_stride + row0;
                     #pragma unroll
-                    for (int nb = 0; nb < 2; ++nb)
+                    for (int nb = 0; nb < 2; ++nb) {
+                        double v[2][RB];
                         #pragma unroll
-                        for (int e = 0; e < 2; ++e) {
-                            const int fl = nb * 8 + t4 * 2 + e;
-                            for (int q = 0; q < op.n_post; ++q) {
-                                const LeafRef lr = lrs[op.n_pre + q];
-                                double v[RB];
-                                leaf_column<RB, NR>(v, p.mt + (size_t)lr.mat * p.mt_stride + row0, load_count(cnt, fl * p.n_leaves + lr.col, p.cnt_width),
-                                                    p.err, p.err_ndev, p.mf);
-                                #pragma unroll
-                                for (int i = 0; i < RB; ++i) acc[i][nb][e] = __dmul_rn(acc[i][nb][e], v[i]);
-                            }
-                        }
+                        for (int e = 0; e < 2; ++e)
+                            leaf_column<RB, NR>(v[e], mt, load_count(cnt, (nb * 8 + t4 * 2 + e) * p.n_leaves + lr.col, p.cnt_width), p.err, p.err_ndev, p.mf);
+                        #pragma unroll
+                        for (int e = 0; e < 2; ++e)
+                            #pragma unroll
+                            for (int i = 0; i < RB; ++i) acc[i][nb][e] = __dmul_rn(acc[i][nb][e], v[e][i]);
+                    }
                 }
                 // exponent bookkeeping of the optional power-of-two rescaling: the product carries the sum of its factors' exponents
                 int* e_par = gexp + (2 + (op.park >= 0 ? op.park + p.n_gspill : -op.park - 1)) * GFT;     // stack entry -> exponent row
@@ -492,37 +494,49 @@ __global__ void __launch_bounds__(pg_threads(NG, GW, PW), 1) prune_kernel(const 
                 const POp op = gops[o];
                 double* dst = gvec + (size_t)(cur ^ 1) * L::VEC_DOUBLES;
                 const LeafRef* lrs = gleaves + op.leaf_begin;
+                // Two families of the warp per round trip, and the first two leaves (a cherry) in the same one: 4 * RPL loads
+                // in flight instead of RPL at a time.
+                constexpr int HF = FPW >= 2 ? 2 : 1;                 // families per batch
                 #pragma unroll
-                for (int fi = 0; fi < FPW; ++fi) {
-                    const int fl = wg * FPW + fi;
-                    double v[RPL];
-                    for (int q = 0; q < op.n_pre; ++q) {
-                        const LeafRef lr = lrs[q];
-                        const double* mt = p.mt + (size_t)lr.mat * p.mt_stride + lane;
-                        const int obs = load_count(cnt, fl * p.n_leaves + lr.col, p.cnt_width);
-                        double w[RPL];
-                        if (p.err == nullptr) {
-                            #pragma unroll
-                            for (int i = 0; i < RPL; ++i) w[i] = __ldg(mt + (size_t)obs * NR + 32 * i);
-                        }
-                        else {
-                            #pragma unroll
-                            for (int i = 0; i < RPL; ++i) w[i] = 0.0;
-                            const int offset = obs - (p.err_ndev - 1) / 2;
-                            for (int d = 0; d < p.err_ndev; ++d) {
-                                const int c = offset + d;
-                                if (c < 0 || c > p.mf) continue;
-                                const double pe = __ldg(p.err + (size_t)obs * p.err_ndev + d);
-                                #pragma unroll
-                                for (int i = 0; i < RPL; ++i) w[i] = __dadd_rn(w[i], __dmul_rn(__ldg(mt + (size_t)c * NR + 32 * i), pe));
-                            }
+                for (int f0 = 0; f0 < FPW; f0 += HF) {
+                    double v[HF][RPL];
+                    {
+                        const LeafRef la = lrs[0];
+                        const bool two = op.n_pre > 1;
+                        const LeafRef lb = two ? lrs[1] : la;
+                        double wa[HF][RPL], wb[HF][RPL];
+                        #pragma unroll
+                        for (int h = 0; h < HF; ++h) {
+                            const int fl = wg * FPW + f0 + h;
+                            leaf_column<RPL, NR, 32>(wa[h], p.mt + (size_t)la.mat * p.mt_stride + lane, load_count(cnt, fl * p.n_leaves + la.col, p.cnt_width),
+                                                     p.err, p.err_ndev, p.mf);
+                            if (two)
+                                leaf_column<RPL, NR, 32>(wb[h], p.mt + (size_t)lb.mat * p.mt_stride + lane,
+                                                         load_count(cnt, fl * p.n_leaves + lb.col, p.cnt_width), p.err, p.err_ndev, p.mf);
                         }
                         #pragma unroll
-                        for (int i = 0; i < RPL; ++i) v[i] = (q == 0) ? w[i] : __dmul_rn(v[i], w[i]);
+                        for (int h = 0; h < HF; ++h)
+                            #pragma unroll
+                            for (int i = 0; i < RPL; ++i) v[h][i] = two ? __dmul_rn(wa[h][i], wb[h][i]) : wa[h][i];
                     }
-                    double* row = dst + (size_t)fl * LDV + lane;
+                    for (int q = 2; q < op.n_pre; ++q) {
+                        const LeafRef lr = lrs[q];
+                        double w[HF][RPL];
+                        #pragma unroll
+                        for (int h = 0; h < HF; ++h)
+                            leaf_column<RPL, NR, 32>(w[h], p.mt + (size_t)lr.mat * p.mt_stride + lane,
+                                                     load_count(cnt, (wg * FPW + f0 + h) * p.n_leaves + lr.col, p.cnt_width), p.err, p.err_ndev, p.mf);
+                        #pragma unroll
+                        for (int h = 0; h < HF; ++h)
+                            #pragma unroll
+                            for (int i = 0; i < RPL; ++i) v[h][i] = __dmul_rn(v[h][i], w[h][i]);
+                    }
                     #pragma unroll
-                    for (int i = 0; i < RPL; ++i) row[32 * i] = v[i];
+                    for (int h = 0; h < HF; ++h) {
+                        double* row = dst + (size_t)(wg * FPW + f0 + h) * LDV + lane;
+                        #pragma unroll
+                        for (int i = 0; i < RPL; ++i) row[32 * i] = v[h][i];
+                    }
                 }
                 if (p.rescale && gtid < GFT) gexp[(cur ^ 1) * GFT + gtid] = 0;
                 cur ^= 1;
