@@ -170,11 +170,12 @@ class CpuReference:
         res = self.orc.infer(self.tree, self.counts[:n], self.rate[:, None] * np.array([[LAMBDA]]), self.freq, self.prior, MF, MRF, self.orc.GAMMA_LINSUM)
         return time.perf_counter() - t0, res["score"]
 
-    def measure(self, n_full, n_slice=CPU_SLICE, timed=1, warm=0):
+    def measure(self, n_full, n_slice=CPU_SLICE, timed=1, warm=0, budget_s=150.0):
         """The reference rebuilds all k x edges transition matrices inside every evaluation (src/gamma_core.cpp:196-197):
         time(F) = a (matrices) + b * F (pruning).  A 32-family run gives a; `timed` runs of the n_slice-family slice give
         b; the value reported is the throughput that gives for the FULL workload, F / (a + b F) — a linear extrapolation
-        in F (families are independent, the gamma path has no de-duplication), flagged as such."""
+        in F (families are independent, the gamma path has no de-duplication), flagged as such.  At most budget_s seconds
+        of slice runs: with many requested steps the later ones repeat the mean of those that were timed (said in `sample`)."""
         n_small = min(len(self.counts), 32)
         n_slice = min(len(self.counts), n_slice)
         t_small, _ = self.run(n_small)
@@ -182,7 +183,10 @@ class CpuReference:
             self.run(n_small)
         values, t_big, score = [], None, None
         a = b = 0.0
-        for _ in range(max(1, timed)):
+        t_start = time.perf_counter()
+        for i in range(max(1, timed)):
+            if i > 0 and time.perf_counter() - t_start + (t_big or 0.0) > budget_s:
+                break
             t_big, score = self.run(n_slice)
             b = max((t_big - t_small) / max(n_slice - n_small, 1), 1e-9)
             a = max(t_small - b * n_small, 0.0)
@@ -190,7 +194,8 @@ class CpuReference:
         return {"value": float(np.mean(values)), "unit": "families/s", "cores": self.cores, "kind": self.kind, "extrapolated": True,
                 "sample": f"infer_family_likelihoods timed on the first {n_small} and {n_slice} config-5 families (k={K}): {t_small:.2f} s and {t_big:.2f} s "
                           f"=> {a:.2f} s per evaluation for the {K}x198 transition matrices + {b * 1e3:.3f} ms per family; value = {n_full} / (a + b*{n_full}), "
-                          f"i.e. linear extrapolation to the full workload (families are independent); measured on the slice alone: {n_slice / t_big:.1f} families/s",
+                          f"i.e. linear extrapolation to the full workload (families are independent); measured on the slice alone: {n_slice / t_big:.1f} families/s; "
+                          f"{len(values)} timed slice run(s) for {max(1, timed)} requested step(s)",
                 "slice_families": n_slice, "slice_seconds": t_big, "slice_families_per_s": n_slice / t_big, "score_of_slice": score,
                 "fixed_s": a, "per_family_s": b, "values": values}
 
