@@ -128,3 +128,19 @@ def test_reference_host_code_with_cuda_pvalues(pv, mammal, tmp_path):
     diff = np.abs(got - pv["pvalues"])
     assert diff.max() <= 1.0 / m["nsim"] + 1e-15
     assert (diff > 0).mean() < 0.02
+
+
+@pytest.mark.gpu
+def test_gpu_root_max_sharded_over_two_devices(pv):
+    """cafe_b200_root_max through a two-device context: the same values, family by family, as on one device."""
+    from cafexp_b200 import engine
+    if engine.device_count() < 2:
+        pytest.skip("needs two visible CUDA devices")
+    m = pv["meta"]
+    for rows in (pv["families"], pv["sim"]):
+        with engine.Engine(pv["tree"], rows, m["max_family_size"], m["max_root_family_size"], device=0) as eng:
+            one = eng.root_max([m["lambda"]])
+        with engine.Engine(pv["tree"], rows, m["max_family_size"], m["max_root_family_size"], device=[0, 1]) as eng:
+            assert "devices=2" in eng.describe()
+            two = eng.root_max([m["lambda"]])
+        assert np.array_equal(one, two)

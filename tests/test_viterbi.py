@@ -83,3 +83,22 @@ def test_reference_host_code_with_cuda_branch_probabilities(vit, mammal, tmp_pat
     assert np.array_equal(probs < 0, vit["probs"] < 0)
     ok = vit["probs"] >= 0
     assert np.allclose(probs[ok], vit["probs"][ok], rtol=1e-12, atol=0)
+
+
+@pytest.mark.gpu
+def test_gpu_branch_probabilities_sharded_over_two_devices(vit):
+    """cafe_b200_branch_probabilities and cafe_b200_reconstruct through a two-device context equal the one-device results."""
+    from cafexp_b200 import engine
+    if engine.device_count() < 2:
+        pytest.skip("needs two visible CUDA devices")
+    m = vit["meta"]
+    sel = np.zeros(len(vit["sizes"]), np.uint8)
+    sel[::3] = 1
+    out = []
+    for dev in (0, [0, 1]):
+        with engine.Engine(vit["tree"], vit["families"], m["max_family_size"], m["max_root_family_size"], device=dev) as eng:
+            prior = orc.prior_uniform(m["max_root_family_size"], None, min(m["max_family_size"], m["max_root_family_size"]) + 1)
+            out.append((eng.branch_probabilities([m["lambda"]], vit["sizes"]), eng.branch_probabilities([m["lambda"]], vit["sizes"], selected=sel),
+                        eng.reconstruct([[m["lambda"]]], prior)))
+    for a, b in zip(out[0], out[1]):
+        assert np.array_equal(a, b)
