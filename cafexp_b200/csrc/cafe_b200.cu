@@ -1058,6 +1058,88 @@ int cafe_b200_set_option(cafe_b200_ctx* c, int option, int value)
     return fail(c, CAFE_B200_ERR_ARG, "unknown option");
 }
 
+// Flat reader of the CAFE tab format: what read_gene_families (src/io.cpp:134-215, "CAFE input
+// format" branch) + gene_family::get_species_size produce, without a std::map per family in between.
+int cafe_b200_read_family_table(const char* path, const char* const* leaf_names, int n_leaves, int32_t* counts, int64_t cap_families,
+                                int64_t* n_families, char* ids, int id_stride)
+{
+    if (!path || !leaf_names || n_leaves < 1 || !n_families) return fail(nullptr, CAFE_B200_ERR_ARG, "bad argument to read_family_table");
+    FILE* f = fopen(path, "rb");
+    if (!f) return fail(nullptr, CAFE_B200_ERR_ARG, std::string("cannot open ") + path);
+    std::string text;
+    {
+        char buf[1 << 16];
+        size_t got;
+        while ((got = fread(buf, 1, sizeof(buf), f)) > 0) text.append(buf, got);
+        fclose(f);
+    }
+    auto lower = [](std::string s) { for (char& ch : s) ch = (char)tolower((unsigned char)ch); return s; };
+    std::map<std::string, int> col_of;                         // species name (lower case, as gene_family keys compare) -> count column
+    for (int l = 0; l < n_leaves; ++l) col_of[lower(leaf_names[l])] = l;
+    size_t pos = 0;
+    auto next_line = [&](size_t& b, size_t& e) {
+        if (pos >= text.size()) return false;
+        b = pos;
+        size_t nl = text.find('\n', pos);
+        e = nl == std::string::npos ? text.size() : nl;
+        pos = e + 1;
+        if (e > b && text[e - 1] == '\r') --e;
+        return true;
+    };
+    size_t b = 0, e = 0;
+    if (!next_line(b, e)) return fail(nullptr, CAFE_B200_ERR_ARG, "No families found");
+    if (text[b] == '#') return fail(nullptr, CAFE_B200_ERR_ARG, "the '#'-header (CAFExp) family format is not supported by the flat reader");
+    // header: Desc <TAB> Family ID <TAB> species ...      (src/io.cpp:160-170: every column from the third on is a species)
+    std::vector<int> col_of_field;
+    {
+        size_t s = b;
+        int field = 0;
+        std::vector<bool> seen(n_leaves, false);
+        while (s <= e) {
+            size_t t = text.find('\t', s);
+            if (t == std::string::npos || t > e) t = e;
+            if (field >= 2) {
+                auto it = col_of.find(lower(text.substr(s, t - s)));
+                col_of_field.push_back(it == col_of.end() ? -1 : it->second);
+                if (it != col_of.end()) seen[it->second] = true;
+            }
+            ++field;
+            s = t + 1;
+        }
+        for (int l = 0; l < n_leaves; ++l)
+            if (!seen[l]) return fail(nullptr, CAFE_B200_ERR_ARG, std::string("species missing from the family table: ") + leaf_names[l]);
+    }
+    int64_t n = 0;
+    while (next_line(b, e)) {
+        if (e == b) continue;
+        // fields: description, id, counts (atoi semantics, src/io.cpp:186)
+        size_t s = b;
+        int field = 0;
+        bool row_ok = n < cap_families && counts;
+        if (row_ok) std::fill(counts + n * n_leaves, counts + (n + 1) * n_leaves, 0);
+        while (s <= e) {
+            size_t t = text.find('\t', s);
+            if (t == std::string::npos || t > e) t = e;
+            if (field == 1 && ids && n < cap_families && id_stride > 0) {
+                const size_t len = std::min<size_t>(t - s, (size_t)id_stride - 1);
+                memcpy(ids + n * id_stride, text.data() + s, len);
+                ids[n * id_stride + len] = 0;
+            }
+            else if (field >= 2 && row_ok && (size_t)(field - 2) < col_of_field.size()) {
+                const int col = col_of_field[field - 2];
+                if (col >= 0) counts[n * n_leaves + col] = atoi(text.c_str() + s);
+            }
+            ++field;
+            s = t + 1;
+        }
+        if (field < 3) continue;                                 // not a family line
+        ++n;
+    }
+    *n_families = n;
+    if (n == 0) return fail(nullptr, CAFE_B200_ERR_ARG, "No families found");
+    return CAFE_B200_OK;
+}
+
 int cafe_b200_plan_schedule(const cafe_b200_tree* tree, int n_slots, int* ops_out, int cap, int* n_ops, int* n_spill)
 {
     if (!tree || tree->n_nodes < 2 || n_slots < 2 || !n_ops) return CAFE_B200_ERR_ARG;

@@ -30,7 +30,7 @@ EXPORTS = [
     "cafe_b200_eval", "cafe_b200_eval_device", "cafe_b200_reconstruct", "cafe_b200_build_matrices", "cafe_b200_matrix_size",
     "cafe_b200_prune_roots", "cafe_b200_launch_count", "cafe_b200_last_timings", "cafe_b200_root_max", "cafe_b200_pvalues",
     "cafe_b200_branch_probabilities", "cafe_b200_create_multi", "cafe_b200_n_devices", "cafe_b200_alloc_pinned", "cafe_b200_free_pinned",
-    "cafe_b200_set_families_ex", "cafe_b200_plan_program", "cafe_b200_describe", "cafe_b200_fetch_category_likelihoods", "cafe_b200_timing_history", "cafe_b200_host_seconds", "cafe_b200_set_build_partition",
+    "cafe_b200_set_families_ex", "cafe_b200_plan_program", "cafe_b200_describe", "cafe_b200_fetch_category_likelihoods", "cafe_b200_timing_history", "cafe_b200_host_seconds", "cafe_b200_set_build_partition", "cafe_b200_read_family_table",
 ]
 
 _dp = C.POINTER(C.c_double)
@@ -93,6 +93,8 @@ def load_library():
     L.cafe_b200_host_seconds.argtypes = [C.c_void_p, _dp]
     L.cafe_b200_set_build_partition.restype = C.c_int
     L.cafe_b200_set_build_partition.argtypes = [C.c_void_p, C.c_int, C.c_int, GATHER_FN, C.c_void_p]
+    L.cafe_b200_read_family_table.restype = C.c_int
+    L.cafe_b200_read_family_table.argtypes = [C.c_char_p, C.POINTER(C.c_char_p), C.c_int, _i32p, C.c_int64, _i64p, C.c_char_p, C.c_int]
     L.cafe_b200_describe.restype = C.c_int
     L.cafe_b200_describe.argtypes = [C.c_void_p, C.c_char_p, C.c_int]
     L.cafe_b200_destroy.argtypes = [C.c_void_p]
@@ -373,6 +375,24 @@ class Engine:
         ms = np.zeros(4)
         self._lib.cafe_b200_last_timings(self._h, _d(ms))
         return {"matrix_build": ms[0], "prune": ms[1], "reduce": ms[2], "reconstruct": ms[3]}
+
+
+def read_family_table(path: str, leaf_names, id_stride: int = 64):
+    """(ids, counts [F][n_leaves] int32) of a CAFE tab-format family table through the library's flat reader
+    (cafe_b200_read_family_table; host only — the same result as hostio.read_gene_families, without Python loops)."""
+    L = load_library()
+    names = (C.c_char_p * len(leaf_names))(*[n.encode() for n in leaf_names])
+    n = C.c_int64()
+    rc = L.cafe_b200_read_family_table(path.encode(), names, len(leaf_names), None, 0, C.byref(n), None, 0)
+    if rc:
+        raise CafeB200Error(f"cafe_b200_read_family_table: {L.cafe_b200_last_error(None).decode()}")
+    counts = np.zeros((n.value, len(leaf_names)), np.int32)
+    ids = C.create_string_buffer(n.value * id_stride)
+    rc = L.cafe_b200_read_family_table(path.encode(), names, len(leaf_names), counts.ctypes.data_as(_i32p), n.value, C.byref(n), ids, id_stride)
+    if rc:
+        raise CafeB200Error(f"cafe_b200_read_family_table: {L.cafe_b200_last_error(None).decode()}")
+    raw = ids.raw
+    return [raw[i * id_stride:(i + 1) * id_stride].split(b"\0", 1)[0].decode() for i in range(n.value)], counts
 
 
 def pvalues(cond, observed, device: int = 0) -> np.ndarray:

@@ -223,6 +223,16 @@ int  cafe_b200_matrix_size(const cafe_b200_ctx* ctx);
  * HOST out [n_families][n_categories][max_root_family_size], index j <-> root size j+1. */
 int  cafe_b200_prune_roots(cafe_b200_ctx* ctx, const double* lambdas, int n_lambdas, int n_categories, double* out);
 
+/* Host-only: flat reader of the CAFE tab-format family table ("Desc<TAB>Family ID<TAB>species..." then one line per family)
+ * = read_gene_families (src/io.cpp:134-215) + gene_family::get_species_size, straight into the row-major count matrix the
+ * engine takes.  Column l of the output is species leaf_names[l] (matched case-insensitively,
+ * src/gene_family.h:10-25); other species columns are ignored; every leaf must have a column.
+ *   counts  out HOST [cap_families][n_leaves] int32, or NULL to only count the families
+ *   ids     out HOST [cap_families][id_stride] NUL-terminated family ids, or NULL
+ * *n_families = families in the file (may exceed cap_families: call again with a larger buffer). */
+int  cafe_b200_read_family_table(const char* path, const char* const* leaf_names, int n_leaves, int32_t* counts, int64_t cap_families,
+                                 int64_t* n_families, char* ids, int id_stride);
+
 /* Host-only (no GPU needed): the op list the reconstruction kernel walks for this tree with n_slots shared-memory
  * slots.  ops_out: [cap][4] = {type, a, b, node}; types: 0 LEAF_SET(a,node) 1 LEAF_MUL
  * 2 GEMM_SET(a,node) 3 GEMM_MUL(a,b,node) 4 SPILL(a->scratch b) 5 FILL(a<-scratch b) 6 (end of node) 7 ROOT(a). */

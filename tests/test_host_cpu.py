@@ -277,3 +277,45 @@ def test_header_is_plain_c(tmp_path):
                           "-lcafe_b200", "-Wl,-rpath," + os.path.join(ROOT, "cafexp_b200")], capture_output=True, text=True)
     assert res.returncode == 0, res.stderr
     assert subprocess.run([str(exe)]).returncode > 0
+
+
+def test_flat_family_reader_matches_the_python_reader(mammal, tmp_path):
+    """cafe_b200_read_family_table (C, host only) against hostio.read_gene_families on the mammal table and on edge cases:
+    extra species columns, shuffled column order, mixed case, CRLF line ends, blank lines."""
+    flat = mammal["tree"]
+    ids = [str(i) for i in np.load(os.path.join(ROOT, "tests", "golden", "mammal_counts.npz"))["ids"]]
+    path = str(tmp_path / "fam.txt")
+    hostio.write_gene_families(path, flat, ids, mammal["counts_all"])
+    want_ids, want = hostio.read_gene_families(path, flat)
+    got_ids, got = engine.read_family_table(path, flat.leaf_names)
+    assert got_ids == want_ids == ids and np.array_equal(got, want) and np.array_equal(got, mammal["counts_all"])
+    tree = hostio.flatten_tree(hostio.parse_newick("((A:1,b:1):1,C:2);"))
+    odd = str(tmp_path / "odd.txt")
+    with open(odd, "w", newline="") as fh:
+        fh.write("Desc\tFamily ID\tc\tX\tB\ta\r\n(null)\tf1\t3\t99\t2\t1\r\n\r\n(null)\tf2\t0\t7\t12x\t5\r\n")
+    got_ids, got = engine.read_family_table(odd, tree.leaf_names)
+    by_species = [{"a": 1, "b": 2, "c": 3}, {"a": 5, "b": 12, "c": 0}]           # atoi semantics: "12x" -> 12 (src/io.cpp:186)
+    want = np.array([[row[name.lower()] for name in tree.leaf_names] for row in by_species], np.int32)
+    assert got_ids == ["f1", "f2"] and np.array_equal(got, want)
+    bad = str(tmp_path / "bad.txt")
+    open(bad, "w").write("Desc\tFamily ID\tA\tb\n(null)\tf1\t1\t2\n")
+    with pytest.raises(engine.CafeB200Error, match="species missing"):
+        engine.read_family_table(bad, tree.leaf_names)
+
+
+def test_create_multi_rejects_bad_input():
+    lib = engine.load_library()
+    handle = C.c_void_p()
+    tree = hostio.flatten_tree(hostio.parse_newick("(A:1,B:1);"))
+    ts, _keep = engine.tree_struct(tree)
+    counts = np.array([[1, 2]], np.int32)
+    devs = np.array([0], np.int32)
+    ip = C.POINTER(C.c_int)
+    args = lambda **kw: (C.byref(handle), C.byref(ts), counts.ctypes.data_as(C.c_void_p), kw.get("bytes", 4), 1, 2, 10, 8,
+                         kw.get("devs", devs).ctypes.data_as(ip) if kw.get("devs", devs) is not None else None, kw.get("n", 1))
+    assert lib.cafe_b200_create_multi(*args(bytes=3)) == -1               # counts of 1, 2 or 4 bytes
+    assert lib.cafe_b200_create_multi(*args(n=0)) == -1                   # at least one device
+    assert lib.cafe_b200_create_multi(*args(devs=None)) == -1
+    # without a GPU every well-formed create fails loudly with ERR_CUDA; with one, a duplicate device is an argument error
+    rc = lib.cafe_b200_create_multi(*args(devs=np.array([0, 0], np.int32), n=2))
+    assert rc == (-1 if lib.cafe_b200_device_count() > 0 else -2)
