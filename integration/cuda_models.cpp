@@ -185,6 +185,7 @@ void cuda_bridge::bind(const std::vector<gene_family>& families)
 void cuda_bridge::bind_rows(const std::vector<int>& rows, size_t n_rows)
 {
     release();
+    ++_generation;
 
     // Identical count rows are evaluated once.  The reference does this for the base model only
     // (build_reference_list, src/base_model.cpp:27-51, O(F^2)); identical inputs give identical outputs for
@@ -377,6 +378,7 @@ double cuda_base_model::infer_family_likelihoods(root_equilibrium_distribution* 
     for (size_t i = 0; i < F; ++i) sum += family_lnl[_bridge.unique_of(i)];
     const double final_likelihood = -sum;
     _results_stale = true;
+    _generation_of_results = _bridge.generation();
     _monitor.Event_InferenceAttempt_Complete(final_likelihood);
     return final_likelihood;
 }
@@ -384,6 +386,8 @@ double cuda_base_model::infer_family_likelihoods(root_equilibrium_distribution* 
 void cuda_base_model::materialize_results()
 {
     if (!_results_stale) return;
+    if (_generation_of_results != _bridge.generation())
+        throw std::runtime_error("cuda_base_model: the device context was rebuilt after the last evaluation; evaluate again before reading results");
     const size_t F = _p_gene_families->size();
     const double* family_lnl = _bridge.family_lnl();
     results.resize(F);
@@ -484,6 +488,7 @@ double cuda_gamma_model::infer_family_likelihoods(root_equilibrium_distribution*
     for (size_t i = 0; i < F; ++i) sum += family_lnl[_bridge.unique_of(i)];
     const double final_likelihood = -sum;
     _results_stale = _cat_lk_stale = true;
+    _generation_of_results = _bridge.generation();
     _monitor.Event_InferenceAttempt_Complete(final_likelihood);
     return final_likelihood;
 }
@@ -491,6 +496,8 @@ double cuda_gamma_model::infer_family_likelihoods(root_equilibrium_distribution*
 const std::vector<std::vector<double>>& cuda_gamma_model::category_likelihoods()
 {
     if (_cat_lk_stale) {
+        if (_generation_of_results != _bridge.generation())
+            throw std::runtime_error("cuda_gamma_model: the device context was rebuilt after the last evaluation; evaluate again before reading results");
         const size_t F = _p_gene_families->size(), k = _last_probs.size();
         const double* cat_lk = _bridge.category_likelihoods();
         _cat_lk.assign(F, std::vector<double>());

@@ -97,6 +97,8 @@ public:
     int max_root_family_size() const { return _mrf; }
     int device_count() const;
     //! device time (CUDA events: matrix build + pruning + reduction) and number of evaluate() calls so far
+    //! incremented whenever the device context (and with it the last evaluation's outputs) is replaced
+    unsigned long generation() const { return _generation; }
     double device_seconds() const { return _device_seconds; }
     long evaluations() const { return _evaluations; }
     //! host wall time so far: [0] bind (flatten + de-duplicate + create the context), [1] inside cafe_b200_eval, of which
@@ -128,6 +130,7 @@ private:
     int _last_k = 0;
     bool _cat_lk_fetched = false;
     std::vector<long long> _failed_idx;
+    unsigned long _generation = 0;
     double _device_seconds = 0.0;
     long _evaluations = 0;
     double _bind_seconds = 0.0, _eval_call_seconds = 0.0;
@@ -162,6 +165,7 @@ public:
 private:
     cuda_bridge _bridge;
     bool _results_stale = false;
+    unsigned long _generation_of_results = 0;      // bridge generation the pending results belong to
 };
 
 class cuda_gamma_model : public gamma_model {
@@ -189,6 +193,7 @@ private:
     std::vector<std::vector<double>> _cat_lk;
     std::vector<double> _last_multipliers, _last_probs;
     bool _results_stale = false, _cat_lk_stale = false, _last_failed = false;
+    unsigned long _generation_of_results = 0;
 
     std::vector<double> cat_probs() const;
 };
