@@ -319,3 +319,49 @@ def test_create_multi_rejects_bad_input():
     # without a GPU every well-formed create fails loudly with ERR_CUDA; with one, a duplicate device is an argument error
     rc = lib.cafe_b200_create_multi(*args(devs=np.array([0, 0], np.int32), n=2))
     assert rc == (-1 if lib.cafe_b200_device_count() > 0 else -2)
+
+
+def _random_newick(rng, n_leaves, shape, max_children):
+    nodes = [f"L{i}" for i in range(n_leaves)]
+    rng.shuffle(nodes)
+    while len(nodes) > 1:
+        k = min(int(rng.integers(2, max_children + 1)), len(nodes))
+        pick = [len(nodes) - 1] + list(range(k - 1)) if shape == "caterpillar" else list(rng.choice(len(nodes), size=k, replace=False))
+        kids = [nodes[i] for i in pick]
+        for i in sorted(pick, reverse=True):
+            nodes.pop(i)
+        rng.shuffle(kids)                                                  # leaves before / between / after internal children
+        nodes.append("(" + ",".join(f"{c}:{float(rng.integers(1, 40))}" for c in kids) + ")")
+    return nodes[0] + ";"
+
+
+@pytest.mark.parametrize("seed", range(24))
+def test_program_on_random_trees(seed):
+    """The pruning program on random binary / n-ary / caterpillar trees, interpreted on the CPU against inference_prune:
+    factor order (leaves before, between and after internal children), stack discipline, depth."""
+    rng = np.random.default_rng(100 + seed)
+    n_leaves = int(rng.choice([2, 3, 5, 9, 17, 30]))
+    tree = hostio.flatten_tree(hostio.parse_newick(_random_newick(rng, n_leaves, str(rng.choice(["random", "caterpillar"])), int(rng.choice([2, 3, 4])))))
+    ops, leaves, depth = plan_program(tree)
+    assert sorted(leaves) == [v for v in range(tree.n_nodes) if tree.leaf_col[v] >= 0]
+    # stack discipline: a pop finds what the matching push left, indices stay below depth, nothing is left at the root
+    live = set()
+    for typ, node, flags, st, lb, n_pre, n_post in ops:
+        if typ != 1:
+            continue
+        if flags & 1:
+            assert st in live
+            live.discard(st)
+        if flags & 2:
+            assert st not in live and st < depth
+            live.add(st)
+    assert not live
+    assert depth == (max((st + 1 for typ, _, flags, st, *_ in ops if typ == 1 and flags), default=0))
+    if all(tree.child_offset[v + 1] - tree.child_offset[v] <= 2 for v in range(tree.n_nodes)):
+        assert depth <= max(0, int(np.ceil(np.log2(max(n_leaves, 2)))) - 1), "binary trees: Sethi-Ullman depth"
+        assert (ops[ops[:, 0] == 1, 5] == 0).all()                         # leaves always after the internal child
+    mf, mrf = 12, 9
+    for _ in range(2):
+        row = rng.integers(0, 6, tree.n_leaves).astype(np.int32)
+        got = interpret_program(tree, ops, leaves, depth, row, [0.03], mf, mrf)
+        np.testing.assert_allclose(got, orc.inference_prune(tree, row, [0.03], mf, mrf), rtol=1e-12, atol=0)
