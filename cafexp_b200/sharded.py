@@ -49,7 +49,12 @@ class ShardedLikelihood:
         """Asynchronous: after this, ``self.result`` holds the global pair on every rank (stream-ordered on CUDA)."""
         self._local_eval(lambdas, prior, cat_probs, mode, self.result)
         if self.world > 1:
+            nvtx = getattr(getattr(__import__("torch"), "cuda", None), "nvtx", None) if self.result.is_cuda else None
+            if nvtx:
+                nvtx.range_push("cafe_b200: allreduce [sum lnL, n_failed]")
             self._dist.all_reduce(self.result, op=self._dist.ReduceOp.SUM, group=self.group)
+            if nvtx:
+                nvtx.range_pop()
 
     def score(self, lambdas, prior, cat_probs, mode) -> float:
         """-lnL of ALL families, identical on every rank; +inf if any family on any rank failed."""
